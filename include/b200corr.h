@@ -1,0 +1,159 @@
+/*
+ * b200corr.h -- C ABI of libb200corr.so: the B200 (sm_100a) cost-volume correlation hot path.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one binding of the reference's two
+ * pybind11 extensions (citations relative to /root/reference):
+ *
+ *   b200corr_sampler_forward   <- spatial_correlation_sampler_backend.forward
+ *                                 models/Pytorch-Correlation-extension/Correlation_Module/
+ *                                 correlation_sampler.cpp:59-87,127 (CUDA: correlation_cuda_kernel.cu:236-273)
+ *   b200corr_sampler_backward  <- spatial_correlation_sampler_backend.backward
+ *                                 correlation_sampler.cpp:89-124,128 (CUDA: correlation_cuda_kernel.cu:275-327)
+ *   b200corr_altcorr_forward   <- alt_cuda_corr.forward   models/alt_cuda_corr/correlation.cpp:23-32,52
+ *                                 (kernel: correlation_kernel.cu:18-119, 260-286)
+ *   b200corr_altcorr_backward  <- alt_cuda_corr.backward  models/alt_cuda_corr/correlation.cpp:35-48,53
+ *                                 (kernel: correlation_kernel.cu:122-256, 288-324)
+ *   b200corr_allpairs_pyramid  <- CorrBlock.__init__ / CorrBlock.corr, models/raft/corr.py:55-64,98-106
+ *                                 (torch.matmul + "/ sqrt(dim)" + 3x F.avg_pool2d)
+ *   b200corr_lookup_forward    <- CorrBlock.__call__, models/raft/corr.py:72-96 +
+ *                                 bilinear_sampler, models/raft/utils/utils.py:62-76 (F.grid_sample)
+ *   b200corr_lookup_backward,
+ *   b200corr_pyramid_backward  <- what autograd derives for corr.py:62-64,72-96
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the current CUDA device
+ *     unless its name starts with `h_` (host array);
+ *   - all tensors are dense row-major ("contiguous" in the reference's CHECK_CONTIGUOUS sense);
+ *   - the library never allocates or frees device memory: outputs and scratch are provided by the
+ *     caller, scratch sizes come from the *_workspace_bytes() queries (host-only, no GPU needed);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and the call returns
+ *     immediately; the reference launches on the legacy default stream instead;
+ *   - return value 0 = success; <0 = error, message via b200corr_last_error() (thread-local).
+ *     The reference raises a C++ exception through TORCH_CHECK; the Python host layer turns the
+ *     error code back into RuntimeError;
+ *   - there is no CPU implementation behind any of these symbols.
+ */
+#ifndef B200CORR_H_
+#define B200CORR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CORR_VERSION 100
+
+/* element types of the sampler entry points (the reference dispatches float/double on CPU and
+ * float/double/half on CUDA, correlation.cpp:104, correlation_cuda_kernel.cu:262) */
+#define B200CORR_F32 0
+#define B200CORR_F64 1
+
+/* precision of the all-pairs contraction */
+#define B200CORR_PREC_TF32 0   /* one tcgen05 kind::tf32 pass, inputs rounded to TF32 (rna)      */
+#define B200CORR_PREC_TF32X3 1 /* 3-pass split-TF32 (hi*hi + hi*lo + lo*hi), ~fp32 accuracy      */
+
+/* coordinate arithmetic of the lookup */
+#define B200CORR_LOOKUP_GRIDSAMPLE 0 /* reproduce utils.py:65-70 + grid_sample's un-normalise     */
+#define B200CORR_LOOKUP_DIRECT 1     /* sample at the pixel coordinate directly (no round trip)   */
+
+int b200corr_version(void);
+const char *b200corr_last_error(void);
+
+/* ---------------------------------------------------------------- spatial correlation sampler */
+
+/* correlation.cpp:90-94 / correlation_cuda_kernel.cu:249-253 */
+int b200corr_sampler_out_size(int in_size, int pad, int kernel, int dilation, int stride);
+
+/* Scratch needed by forward / backward for this problem (0 is a valid answer). */
+size_t b200corr_sampler_forward_workspace_bytes(int B, int C, int H, int W, int kH, int kW,
+                                                int patchH, int patchW, int padH, int padW,
+                                                int dilationH, int dilationW, int dilation_patchH,
+                                                int dilation_patchW, int dH, int dW, int dtype);
+size_t b200corr_sampler_backward_workspace_bytes(int B, int C, int H, int W, int kH, int kW,
+                                                 int patchH, int patchW, int padH, int padW,
+                                                 int dilationH, int dilationW, int dilation_patchH,
+                                                 int dilation_patchW, int dH, int dW, int dtype);
+
+/* out[B, patchH, patchW, oH, oW] = sum_{c,i,j} in1[b,c,y1,x1] * in2[b,c,y1+dy,x1+dx]
+ * (SURVEY.md section 8(0) S1).  Every element of `out` is written.  The 12 integers are in the
+ * order of the reference's backend.forward(...) call (spatial_correlation_sampler.py:68-83). */
+int b200corr_sampler_forward(const void *in1, const void *in2, void *out, void *workspace,
+                             size_t workspace_bytes, int B, int C, int H, int W, int kH, int kW,
+                             int patchH, int patchW, int padH, int padW, int dilationH,
+                             int dilationW, int dilation_patchH, int dilation_patchW, int dH, int dW,
+                             int dtype, void *stream);
+
+/* grad_in1, grad_in2 [B, C, H, W] from grad_out [B, patchH, patchW, oH, oW]; every element of both
+ * gradients is written (gather form, no atomics, deterministic). */
+int b200corr_sampler_backward(const void *in1, const void *in2, const void *grad_out,
+                              void *grad_in1, void *grad_in2, void *workspace,
+                              size_t workspace_bytes, int B, int C, int H, int W, int kH, int kW,
+                              int patchH, int patchW, int padH, int padW, int dilationH,
+                              int dilationW, int dilation_patchH, int dilation_patchW, int dH,
+                              int dW, int dtype, void *stream);
+
+/* 1 if the problem runs on the TMA-staged register-blocked kernels, 0 if on the generic kernels. */
+int b200corr_sampler_uses_fast_path(int B, int C, int H, int W, int kH, int kW, int patchH,
+                                    int patchW, int padH, int padW, int dilationH, int dilationW,
+                                    int dilation_patchH, int dilation_patchW, int dH, int dW,
+                                    int dtype, int backward);
+
+/* ---------------------------------------------------------------- RAFT CorrBlock */
+
+/* Level l has shape (B*H*W, 1, H_l, W_l), H_0 = H, H_{l+1} = H_l / 2 (floor), same for W. */
+size_t b200corr_allpairs_workspace_bytes(int B, int C, int H, int W, int precision);
+
+/* h_levels[l] = device pointer of level l (l < num_levels <= 8).
+ * level0[b,p1,p2] = scale * sum_c f1[b,c,p1] * f2[b,c,p2]; level l+1 = avg_pool2d(level l, 2, 2). */
+int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_levels,
+                              int num_levels, int B, int C, int H, int W, float scale,
+                              int precision, void *workspace, size_t workspace_bytes, void *stream);
+
+/* out[B, num_levels*(2r+1)^2, H, W]; coords[B, 2, H, W] (channel 0 = x).  Channel index
+ * l*(2r+1)^2 + i*(2r+1) + j, i = x-offset index, j = y-offset index (corr.py:80-86). */
+int b200corr_lookup_forward(const float *const *h_levels, int num_levels, const float *coords,
+                            float *out, int B, int H, int W, int radius, int mode, void *stream);
+
+/* Accumulates (+=) d(out)/d(level l) into h_grad_levels[l] (caller zero-initialises once per
+ * CorrBlock; several lookups of the same block accumulate).  Coordinates get no gradient
+ * (the reference detaches them, models/raft/raft.py:188). */
+int b200corr_lookup_backward(float *const *h_grad_levels, int num_levels, const float *coords,
+                             const float *grad_out, int B, int H, int W, int radius, int mode,
+                             void *stream);
+
+/* Folds the pooled-level gradients down into level 0: for l = num_levels-1 .. 1,
+ * grad_levels[l-1][.., y, x] += grad_levels[l][.., y/2, x/2] / 4 (backward of avg_pool2d). */
+int b200corr_pyramid_backward(float *const *h_grad_levels, int num_levels, int B, int H, int W,
+                              void *stream);
+
+/* ---------------------------------------------------------------- alt_cuda_corr */
+
+/* fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C] (NHWC), coords [B,N,H1,W1,2] -> corr [B,N,(2r+1)^2,H1,W1],
+ * channel = ix*(2r+1) + iy, no 1/sqrt(C) factor (correlation_kernel.cu:92-114; corr.py:137). */
+int b200corr_altcorr_forward(const float *fmap1, const float *fmap2, const float *coords,
+                             float *corr, int B, int N, int H1, int W1, int H2, int W2, int C,
+                             int radius, void *stream);
+
+/* fmap1_grad [B,H1,W1,C] and fmap2_grad [B,H2,W2,C] are fully written (fmap2_grad is zeroed
+ * inside the call, then scatter-added); coords_grad [B,N,H1,W1,2] is set to zero, as in the
+ * reference (correlation_kernel.cu:307). */
+int b200corr_altcorr_backward(const float *fmap1, const float *fmap2, const float *coords,
+                              const float *corr_grad, float *fmap1_grad, float *fmap2_grad,
+                              float *coords_grad, int B, int N, int H1, int W1, int H2, int W2,
+                              int C, int radius, void *stream);
+
+/* ---------------------------------------------------------------- diagnostics */
+
+/* Runs `iters` dependent FP32 FMAs per thread on every SM and returns the achieved TFLOP/s in
+ * *tflops (used by bench.py for the FP32-pipe roofline denominator). */
+int b200corr_measure_fp32_peak(int iters, float *tflops, void *stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t b200corr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CORR_H_ */

@@ -1,0 +1,57 @@
+"""SM probes (run on the GPU box): LDS.128 multicast cost, FP32 FFMA peak, first sampler timings."""
+import ctypes
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from understanding_flow_robustness_b200 import _lib, spatial_correlation_sample
+
+L = _lib.lib()
+res = {}
+st = _lib.current_stream(torch.device("cuda:0"))
+v = ctypes.c_float()
+for warps in (4, 8, 16):
+    for pat in range(9):
+        _lib.check(L.b200corr_probe_lds(pat, warps, 2000, ctypes.byref(v), st), "probe_lds")
+        res[f"lds_p{pat}_w{warps}"] = round(v.value, 3)
+_lib.check(L.b200corr_measure_fp32_peak(20000, ctypes.byref(v), st), "fp32 peak")
+res["fp32_peak_tflops"] = round(v.value, 2)
+_lib.check(L.b200corr_probe_ffma_toeplitz(2000, ctypes.byref(v), st), "toeplitz")
+res["ffma_toeplitz_tflops"] = round(v.value, 2)
+print(json.dumps(res, indent=1))
+
+
+def timeit(fn, n=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+if "--sampler" in sys.argv:
+    for B in (1, 8):
+        a = torch.randn(B, 256, 48, 160, device="cuda", requires_grad=True)
+        b = torch.randn(B, 256, 48, 160, device="cuda", requires_grad=True)
+        g = torch.randn(B, 21, 21, 48, 160, device="cuda")
+        from understanding_flow_robustness_b200 import backend
+        q = (1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1)
+        tf = timeit(lambda: backend.forward(a.detach(), b.detach(), *q))
+        tb = timeit(lambda: backend.backward(a.detach(), b.detach(), g, *q))
+        inb = 256 * 788 * 3140 * 2 * B
+        print(json.dumps({"B": B, "fwd_ms": round(tf, 4), "bwd_ms": round(tb, 4),
+                          "fwd_inbounds_tflops": round(inb / tf / 1e9, 2),
+                          "bwd_inbounds_tflops": round(2 * inb / tb / 1e9, 2),
+                          "pairs_per_s": round(B / (tf + tb) * 1e3, 1)}))

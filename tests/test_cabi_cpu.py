@@ -1,0 +1,52 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/b200corr.h declares,
+and the host-only entry points behave (no compute calls here: there is no GPU)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "b200corr.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200corr_\w+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from understanding_flow_robustness_b200 import build, _lib
+    build.build()
+    return _lib.lib()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 10
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_host_only_entry_points(lib):
+    assert lib.b200corr_version() == 100
+    # correlation.cpp:90-94
+    assert lib.b200corr_sampler_out_size(48, 0, 1, 1, 1) == 48
+    assert lib.b200corr_sampler_out_size(10, 5, 3, 2, 2) == 8
+    assert lib.b200corr_sampler_out_size(2, 0, 5, 1, 1) == -1
+    # dispatch rule: FlowNetC / PWC structure -> register-blocked kernels, everything else generic
+    f = lib.b200corr_sampler_uses_fast_path
+    assert f(8, 256, 48, 160, 1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1, 0, 0) == 1
+    assert f(8, 256, 48, 160, 1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1, 0, 1) == 1
+    assert f(8, 196, 48, 160, 1, 1, 9, 9, 0, 0, 1, 1, 1, 1, 1, 1, 0, 1) == 0   # C % 128 != 0 backward
+    assert f(1, 10, 10, 10, 3, 3, 3, 3, 5, 5, 2, 2, 2, 2, 2, 2, 1, 0) == 0
+    assert f(1, 8, 12, 13, 1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1, 0, 0) == 0    # W % 4 != 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "understanding_flow_robustness_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("# oracle", ""), os.path.join(dirpath, f)

@@ -1,0 +1,59 @@
+"""ctypes binding of libb200corr.so (the C ABI declared in include/b200corr.h)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200corr.so")
+
+_lib = None
+
+c_int, c_void_p, c_size_t, c_float = ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float
+
+# name -> (restype, argtypes); every symbol include/b200corr.h declares
+PROTOTYPES = {
+    "b200corr_version": (c_int, []),
+    "b200corr_last_error": (ctypes.c_char_p, []),
+    "b200corr_sampler_out_size": (c_int, [c_int] * 5),
+    "b200corr_sampler_forward_workspace_bytes": (c_size_t, [c_int] * 17),
+    "b200corr_sampler_backward_workspace_bytes": (c_size_t, [c_int] * 17),
+    "b200corr_sampler_forward": (c_int, [c_void_p] * 4 + [c_size_t] + [c_int] * 17 + [c_void_p]),
+    "b200corr_sampler_backward": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 17 + [c_void_p]),
+    "b200corr_sampler_uses_fast_path": (c_int, [c_int] * 18),
+    "b200corr_measure_fp32_peak": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p]),
+    "b200corr_launch_count": (ctypes.c_uint64, []),
+    "b200corr_probe_lds": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float), c_void_p]),
+    "b200corr_probe_ffma_toeplitz": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p]),
+}
+
+
+def lib():
+    """Load the shared library once.  Fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m understanding_flow_robustness_b200.build` "
+                "(there is no fallback implementation)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().b200corr_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed ({code}): {msg}")
+
+
+def current_stream(device):
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr())

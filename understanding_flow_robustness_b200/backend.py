@@ -1,0 +1,79 @@
+"""Drop-in for the reference's pybind module `spatial_correlation_sampler_backend`.
+
+Reference: models/Pytorch-Correlation-extension/Correlation_Module/correlation_sampler.cpp:59-129
+(`forward(input1, input2, kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
+dilation_patchH, dilation_patchW, dH, dW)` and `backward(input1, input2, grad_output, <same 12>)`).
+Same argument order and meaning; the checks the reference does with TORCH_CHECK
+(CHECK_CUDA / CHECK_CONTIGUOUS / CHECK_SAME_DEVICE, :31-34,69-75,101-107) raise RuntimeError here
+too, plus shape/dtype validation the reference leaves out.  CUDA tensors only: the reference's CPU
+branch (:76-86) has no counterpart in this package.
+"""
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: 0, torch.float64: 1}
+
+
+def _check_inputs(who, *tensors):
+    first = tensors[0]
+    for t in tensors:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{who}: expected torch.Tensor, got {type(t)}")
+        if not t.is_cuda:
+            raise RuntimeError(f"{who}: input must be a CUDA tensor (this build has no CPU path)")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{who}: input must be contiguous")
+        if t.device != first.device:
+            raise RuntimeError(f"{who}: inputs must be on the same device")
+        if t.dtype != first.dtype:
+            raise RuntimeError(f"{who}: inputs must have the same dtype")
+    if first.dtype not in _DTYPES:
+        raise RuntimeError(f"{who}: unsupported dtype {first.dtype} (float32 / float64)")
+    return _DTYPES[first.dtype]
+
+
+def output_size(size, pad, kernel, dilation, stride):
+    """correlation_cuda_kernel.cu:249-253 / correlation.cpp:90-94"""
+    return (size + 2 * pad - ((kernel - 1) * dilation + 1)) // stride + 1
+
+
+def forward(input1, input2, kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
+            dilation_patchH, dilation_patchW, dH, dW):
+    dt = _check_inputs("correlation forward", input1, input2)
+    if input1.dim() != 4 or input1.shape != input2.shape:
+        raise RuntimeError("correlation forward: input1 and input2 must both be (B, C, H, W) of the same shape")
+    B, C, H, W = input1.shape
+    oH = output_size(H, padH, kH, dilationH, dH)
+    oW = output_size(W, padW, kW, dilationW, dW)
+    if oH < 0 or oW < 0:
+        raise RuntimeError("correlation forward: kernel does not fit the padded input")
+    out = torch.empty((B, patchH, patchW, oH, oW), dtype=input1.dtype, device=input1.device)
+    with torch.cuda.device(input1.device):
+        code = _lib.lib().b200corr_sampler_forward(
+            _lib.ptr(input1), _lib.ptr(input2), _lib.ptr(out), None, 0, B, C, H, W, kH, kW, patchH,
+            patchW, padH, padW, dilationH, dilationW, dilation_patchH, dilation_patchW, dH, dW, dt,
+            _lib.current_stream(input1.device))
+    _lib.check(code, "b200corr_sampler_forward")
+    return out
+
+
+def backward(input1, input2, grad_output, kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
+             dilation_patchH, dilation_patchW, dH, dW):
+    grad_output = grad_output.contiguous()
+    dt = _check_inputs("correlation backward", input1, input2, grad_output)
+    B, C, H, W = input1.shape
+    oH = output_size(H, padH, kH, dilationH, dH)
+    oW = output_size(W, padW, kW, dilationW, dW)
+    if tuple(grad_output.shape) != (B, patchH, patchW, oH, oW):
+        raise RuntimeError(f"correlation backward: grad_output shape {tuple(grad_output.shape)} != "
+                           f"{(B, patchH, patchW, oH, oW)}")
+    g1 = torch.empty_like(input1)
+    g2 = torch.empty_like(input2)
+    with torch.cuda.device(input1.device):
+        code = _lib.lib().b200corr_sampler_backward(
+            _lib.ptr(input1), _lib.ptr(input2), _lib.ptr(grad_output), _lib.ptr(g1), _lib.ptr(g2),
+            None, 0, B, C, H, W, kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
+            dilation_patchH, dilation_patchW, dH, dW, dt, _lib.current_stream(input1.device))
+    _lib.check(code, "b200corr_sampler_backward")
+    return [g1, g2]

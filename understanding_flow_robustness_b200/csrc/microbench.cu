@@ -1,0 +1,146 @@
+// microbench.cu -- small probes of the sm_100a SM used to size the sampler kernels:
+//   * shared-memory LDS.128 throughput under different lane->address sharing patterns
+//     (how many wavefronts a multicast 128-bit load costs);
+//   * FP32 FFMA rate of the register-blocked Toeplitz update the sampler forward issues
+//     (acc[t][k] += a[t] * v[t + 2k], 8 x 21 accumulators per thread).
+// Diagnostics only; nothing on the data path calls these.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int lds_pattern_chunk(int pattern, int lane) {
+  switch (pattern) {
+    case 0: return lane;                    // 32 distinct 16-B chunks (512 B)
+    case 1: return lane >> 2;               // 8 distinct, 4 consecutive lanes share
+    case 2: return lane & 7;                // 8 distinct, lanes l, l+8, l+16, l+24 share
+    case 3: return lane >> 3;               // 4 distinct
+    case 4: return 0;                       // 1 distinct (full broadcast)
+    case 5: return (lane & 7) * 21;         // 8 distinct rows, row stride 84 floats (= 21 chunks)
+    case 6: return (lane >> 2) * 21;        // 8 distinct rows, consecutive lanes share
+    case 7: return (lane % 11) * 21;        // 11 distinct rows (176 B)
+    case 8: return (lane & 15);             // 16 distinct
+    default: return lane;
+  }
+}
+
+__global__ void __launch_bounds__(512) lds_probe_kernel(float *sink, int iters, int pattern,
+                                                        unsigned long long *cycles) {
+  extern __shared__ float4 sm4[];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+    sm4[i] = make_float4((float)i, 1.f, 2.f, 3.f);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t base =
+      b200dev::smem_u32(sm4) + 16u * (uint32_t)(lds_pattern_chunk(pattern, lane) + (warp & 3) * 256);
+  float a0 = 0.f, a1 = 0.f;
+  unsigned long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      float x, y, z, w;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(x), "=f"(y), "=f"(z), "=f"(w)
+                   : "r"(base + (uint32_t)(u & 1) * 16u * 1024u));
+      a0 += x;
+      a1 += w;
+    }
+  }
+  unsigned long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (a0 + a1 == 123.456f) sink[0] = a0;
+}
+
+// 8 x 21 Toeplitz register update, operands refreshed from registers only.
+__global__ void __launch_bounds__(256, 1) ffma_toeplitz_kernel(float *sink, int iters, float seed) {
+  float acc[8][21];
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+#pragma unroll
+    for (int k = 0; k < 21; ++k) acc[t][k] = 0.f;
+  float a[8], v[48];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) a[t] = seed + threadIdx.x + t;
+#pragma unroll
+  for (int m = 0; m < 48; ++m) v[m] = seed * m + 1.f;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+      for (int k = 0; k < 21; ++k) acc[t][k] = fmaf(a[t], v[t + 2 * k], acc[t][k]);
+    // cheap operand refresh so the loop body is not hoisted (8 + 12 non-FMA instructions)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) a[t] = __int_as_float(__float_as_int(a[t]) ^ (it << 3));
+#pragma unroll
+    for (int m = 0; m < 48; m += 4) v[m] = __int_as_float(__float_as_int(v[m]) ^ it);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+#pragma unroll
+    for (int k = 0; k < 21; ++k) s += acc[t][k];
+  if (s == 12345.678f) sink[0] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+// cycles per LDS.128 warp-instruction per SM at `warps` resident warps (one CTA per SM).
+int b200corr_probe_lds(int pattern, int warps, int iters, float *cycles_per_lds, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK(warps >= 1 && warps <= 16 && iters > 0 && cycles_per_lds, "probe_lds: bad arguments");
+  const int blocks = b200::num_sms();
+  float *sink = nullptr;
+  unsigned long long *cyc = nullptr;
+  B200_CUDA(cudaMalloc(&sink, sizeof(float)));
+  B200_CUDA(cudaMalloc(&cyc, sizeof(unsigned long long) * blocks));
+  const size_t smem = 2048 * sizeof(float4);
+  lds_probe_kernel<<<blocks, warps * 32, smem, stream>>>(sink, 4, pattern, cyc);
+  lds_probe_kernel<<<blocks, warps * 32, smem, stream>>>(sink, iters, pattern, cyc);
+  B200_LAUNCH_OK("lds_probe_kernel");
+  B200_CUDA(cudaStreamSynchronize(stream));
+  unsigned long long h[256];
+  B200_CUDA(cudaMemcpy(h, cyc, sizeof(unsigned long long) * (blocks < 256 ? blocks : 256),
+                       cudaMemcpyDeviceToHost));
+  double sum = 0;
+  const int n = blocks < 256 ? blocks : 256;
+  for (int i = 0; i < n; ++i) sum += (double)h[i];
+  *cycles_per_lds = (float)(sum / n / ((double)iters * 16 * warps));
+  cudaFree(sink);
+  cudaFree(cyc);
+  return 0;
+}
+
+// achieved TFLOP/s of the 8x21 Toeplitz FFMA block (256 threads/SM, 168 accumulators each)
+int b200corr_probe_ffma_toeplitz(int iters, float *tflops, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK(iters > 0 && tflops, "probe_ffma_toeplitz: bad arguments");
+  float *sink = nullptr;
+  B200_CUDA(cudaMalloc(&sink, sizeof(float)));
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0));
+  B200_CUDA(cudaEventCreate(&e1));
+  const int blocks = b200::num_sms() * 4;
+  ffma_toeplitz_kernel<<<blocks, 256, 0, stream>>>(sink, 8, 0.f);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    B200_CUDA(cudaEventRecord(e0, stream));
+    ffma_toeplitz_kernel<<<blocks, 256, 0, stream>>>(sink, iters, 0.f);
+    B200_CUDA(cudaEventRecord(e1, stream));
+    B200_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  B200_LAUNCH_OK("ffma_toeplitz_kernel");
+  *tflops = (float)(2.0 * 168 * (double)iters * blocks * 256 / (best * 1e-3) / 1e12);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,358 @@
+// sampler_fast_bwd.cu -- register-blocked, TMA-staged backward of the spatial correlation sampler
+// for the FlowNetC / PWC-Net call-site structure (kernel_size 1, stride 1, padding 0):
+//
+//   WHICH == 1:  gIn1[n,c,h,w] = sum_{e,k} G[n,e,k,h,w]           * in2[n,c,h+e*dpH, w+(k-RW)*dpW]
+//   WHICH == 2:  gIn2[n,c,y,x] = sum_{e,k} G[n,e,k,y-e*dpH,x-dxk] * in1[n,c,y-e*dpH, x-dxk]
+//
+// (e = row displacement index - RH, dxk = (k-RW)*dpW.)  Gather form, no atomics, deterministic;
+// replaces correlation_cuda_backward_kernel_input1/2 (correlation_cuda_kernel.cu:87-233, one launch
+// per batch sample, 25-thread blocks, thread-(0,0) serial reduction).
+//
+// Both gradients are the same contraction: for a pixel row s and a source row R of the OTHER
+// feature map (e = R - s for gIn1, e = s - R for gIn2) and 8 consecutive pixels t,
+//     acc[t][c] += Gk[k'][t] * other[c][R][x0 + t + k'*dpW - HALO],   k' = 0..PW-1
+// with Gk the grad_output row re-indexed (gIn2 walks k backwards and reads G at the source pixel).
+// One thread owns 8 pixels x 8 channels (64 accumulators) and, per source row, holds half of the
+// PW x 8 grad_output coefficients in registers (two passes over k), so each 16-byte window load of
+// `other` feeds ~12 FFMA.  A warp is 4 pixel rows x 8 interleaved channels: the 4 row-lanes read the
+// same `other` address (multicast), the 8 channel-lanes read the same grad_output address.
+// Source rows outside the image are never visited, so work tracks the in-bounds MAC count.
+// Persistent CTAs, one per SM, a TMA/mbarrier ring over source rows that runs across units.
+#include "sampler_fast.cuh"
+
+namespace {
+using namespace b200dev;
+
+constexpr int odd4b(int x) {
+  int c = (x + 3) / 4;
+  if (c % 2 == 0) ++c;
+  return 4 * c;
+}
+constexpr int round_up_c(int a, int b) { return (a + b - 1) / b * b; }
+
+template <int PH_, int PW_, int DPW_, int WHICH_>
+struct BwdCfg {
+  static constexpr int PH = PH_, PW = PW_, DPW = DPW_, WHICH = WHICH_;
+  static constexpr int T = 8, NCH = 8, CSETS = 2, CGROUPS = 4;
+  static constexpr int CH_UNIT = 8 * NCH * CSETS;     // 128 channels per unit
+  static constexpr int COLS = CGROUPS * T;            // 32 pixels per unit row
+  static constexpr int RH = (PH - 1) / 2, RW = (PW - 1) / 2;
+  static constexpr int HALO = RW * DPW;
+  static constexpr int WIN = T + (PW - 1) * DPW;
+  static_assert(WIN % 4 == 0, "window must be whole 16-byte chunks");
+  static constexpr int NC = odd4b(COLS + (PW - 1) * DPW);   // staged columns of `other`
+  static constexpr int OTHER_FLOATS = CH_UNIT * NC;
+  // grad_output staging: WHICH 1 -> four separate [PW][GC] boxes, the box of row-lane li shifted
+  // left by 4*li columns so the four lanes hit different banks; WHICH 2 -> one [4][PW][NC] box.
+  static constexpr int GC = COLS + 12;
+  static constexpr int GLI = round_up_c(PW * GC, 32);
+  static constexpr int G_FLOATS = WHICH == 1 ? 4 * GLI : round_up_c(4 * PW * NC, 32);
+  static constexpr int STAGE_FLOATS = OTHER_FLOATS + G_FLOATS;
+  static constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
+  static_assert((OTHER_FLOATS * 4) % 128 == 0 && STAGE_BYTES % 128 == 0 && (GLI * 4) % 128 == 0,
+                "TMA destination alignment");
+  static constexpr int NST = (4 * STAGE_BYTES + 128 <= 227 * 1024) ? 4 : 3;
+  static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 128;
+  static constexpr int KA = (PW + 1) / 2;             // first k' pass: [0, KA), second: [KA, PW)
+};
+
+struct BwdParams {
+  int B, C, H, W, dpH, NCT, NCB, total_units;
+  b200::SamplerGroups g;   // prefix[] unused here (every group has NCT*NCB units)
+};
+
+struct BUnit {
+  int n, rp, s0, NS, c0, cb, Rlo, nsteps;
+};
+
+template <class Cfg>
+__device__ __forceinline__ void decode_bunit(const BwdParams &p, int u, BUnit &x) {
+  const int per_group = p.NCT * p.NCB;
+  const int ups = p.g.ngroups * per_group;
+  x.n = u / ups;
+  int r = u - x.n * ups;
+  const int gi = r / per_group;
+  r -= gi * per_group;
+  x.c0 = (r / p.NCB) * Cfg::COLS;
+  x.cb = r % p.NCB;
+  x.rp = p.g.rp[gi];
+  x.s0 = p.g.s0[gi];
+  x.NS = (p.H - x.rp + p.dpH - 1) / p.dpH;
+  const int s_last = x.s0 + 3 < x.NS - 1 ? x.s0 + 3 : x.NS - 1;
+  x.Rlo = x.s0 - Cfg::RH > 0 ? x.s0 - Cfg::RH : 0;
+  const int Rhi = s_last + Cfg::RH < x.NS - 1 ? s_last + Cfg::RH : x.NS - 1;
+  x.nsteps = Rhi - x.Rlo + 1;
+}
+
+// One k' pass [K0, K1): coefficients to registers, then stream the `other` window per channel.
+template <class Cfg, int K0, int K1>
+__device__ __forceinline__ void bwd_pass(float (&acc)[Cfg::T][Cfg::NCH], const float *gs,
+                                         const float *vb) {
+  constexpr int DPW = Cfg::DPW, PW = Cfg::PW, NC = Cfg::NC, T = Cfg::T;
+  constexpr int NK = K1 - K0;
+  float Gr[NK][T];
+#pragma unroll
+  for (int kk = 0; kk < NK; ++kk) {
+    const int k = K0 + kk;
+    if (Cfg::WHICH == 1) {
+      const float4 g0 = lds128(gs + k * Cfg::GC);
+      const float4 g1 = lds128(gs + k * Cfg::GC + 4);
+      Gr[kk][0] = g0.x; Gr[kk][1] = g0.y; Gr[kk][2] = g0.z; Gr[kk][3] = g0.w;
+      Gr[kk][4] = g1.x; Gr[kk][5] = g1.y; Gr[kk][6] = g1.z; Gr[kk][7] = g1.w;
+    } else {
+      const float *gp = gs + (PW - 1 - k) * NC + k * DPW;
+      if ((k * DPW) % 4 == 0) {
+        const float4 g0 = lds128(gp), g1 = lds128(gp + 4);
+        Gr[kk][0] = g0.x; Gr[kk][1] = g0.y; Gr[kk][2] = g0.z; Gr[kk][3] = g0.w;
+        Gr[kk][4] = g1.x; Gr[kk][5] = g1.y; Gr[kk][6] = g1.z; Gr[kk][7] = g1.w;
+      } else if ((k * DPW) % 2 == 0) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float2 g = *reinterpret_cast<const float2 *>(gp + 2 * h);
+          Gr[kk][2 * h] = g.x;
+          Gr[kk][2 * h + 1] = g.y;
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < T; ++t) Gr[kk][t] = gp[t];
+      }
+    }
+  }
+  constexpr int MB = (K0 * DPW) / 4 * 4;            // first window float this pass touches (16-B aligned)
+  constexpr int ME = T + (K1 - 1) * DPW;            // one past the last
+  constexpr int NL = (ME - MB + 3) / 4;
+#pragma unroll
+  for (int ci = 0; ci < Cfg::NCH; ++ci) {
+#pragma unroll
+    for (int sg = 0; sg < NL; ++sg) {
+      const float4 v4 = lds128(vb + ci * 8 * NC + MB + 4 * sg);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int d = MB + 4 * sg + uu - t;  // = k' * DPW
+          if (d >= 0 && d % DPW == 0 && d / DPW >= K0 && d / DPW < K1)
+            acc[t][ci] = fmaf(Gr[d / DPW - K0][t], v[uu], acc[t][ci]);
+        }
+      }
+    }
+  }
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(256, 1)
+sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_constant__ CUtensorMap map_g,
+                   float *__restrict__ gin, const BwdParams p) {
+  constexpr int NST = Cfg::NST, RH = Cfg::RH, PW = Cfg::PW, NC = Cfg::NC, T = Cfg::T;
+  extern __shared__ __align__(128) float smem[];
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + NST * Cfg::STAGE_FLOATS);
+  uint64_t *empty_bar = full_bar + NST;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int li = lane >> 3, lj = lane & 7;
+  const int cgw = warp & 3, cset = warp >> 2;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map_other);
+    tma_prefetch_desc(&map_g);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 8);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int nunits = p.total_units;
+
+  // ---- producer (thread 0): walks (unit, source row) NST-1 steps ahead of the math
+  int pu = blockIdx.x, ps = 0;
+  uint32_t pq = 0;
+  BUnit px;
+  if (tid == 0 && pu < nunits) decode_bunit<Cfg>(p, pu, px);
+  auto issue = [&]() {
+    if (pu >= nunits) return;
+    const int st = pq % NST;
+    float *dst = smem + st * Cfg::STAGE_FLOATS;
+    const int R = px.Rlo + ps;
+    uint32_t bytes = Cfg::OTHER_FLOATS * 4;
+    if (Cfg::WHICH == 1) {
+      for (int l = 0; l < 4; ++l) {
+        const int s = px.s0 + l, e = R - s;
+        if (s < px.NS && e >= -RH && e <= RH) bytes += PW * Cfg::GC * 4;
+      }
+    } else {
+      bytes += 4 * PW * NC * 4;
+    }
+    mbar_arrive_expect_tx(&full_bar[st], bytes);
+    tma_load_3d(dst, &map_other, &full_bar[st], px.c0 - Cfg::HALO, R * p.dpH + px.rp,
+                px.n * p.C + px.cb * Cfg::CH_UNIT);
+    float *gd = dst + Cfg::OTHER_FLOATS;
+    if (Cfg::WHICH == 1) {
+      for (int l = 0; l < 4; ++l) {
+        const int s = px.s0 + l, e = R - s;
+        if (s < px.NS && e >= -RH && e <= RH)
+          tma_load_5d(gd + l * Cfg::GLI, &map_g, &full_bar[st], px.c0 - 4 * l, s * p.dpH + px.rp, 0,
+                      e + RH, px.n);
+      }
+    } else {
+      tma_load_5d(gd, &map_g, &full_bar[st], px.c0 - Cfg::HALO, R * p.dpH + px.rp, 0,
+                  px.s0 - R + RH, px.n);
+    }
+    ++pq;
+    if (++ps == px.nsteps) {
+      ps = 0;
+      pu += gridDim.x;
+      if (pu < nunits) decode_bunit<Cfg>(p, pu, px);
+    }
+  };
+  if (tid == 0)
+    for (int s = 0; s < NST - 1; ++s) issue();
+
+  uint32_t q = 0;
+  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    BUnit x;
+    decode_bunit<Cfg>(p, u, x);
+    const int s = x.s0 + li;
+    // per-thread offsets inside a stage
+    const int offv = (cset * 64 + lj) * NC + cgw * T;
+    const int offg = Cfg::OTHER_FLOATS +
+                     (Cfg::WHICH == 1 ? li * Cfg::GLI + cgw * T + 4 * li : li * PW * NC + cgw * T);
+
+    float acc[T][Cfg::NCH];
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int c = 0; c < Cfg::NCH; ++c) acc[t][c] = 0.f;
+
+    for (int step = 0; step < x.nsteps; ++step, ++q) {
+      const int st = q % NST;
+      if (tid == 0) {
+        if (q > 0) mbar_wait(&empty_bar[(q - 1) % NST], ((q - 1) / NST) & 1);
+        issue();
+      }
+      mbar_wait(&full_bar[st], (q / NST) & 1);
+      const int R = x.Rlo + step;
+      const int e = Cfg::WHICH == 1 ? R - s : s - R;
+      if (s < x.NS && e >= -RH && e <= RH) {
+        const float *vb = smem + st * Cfg::STAGE_FLOATS + offv;
+        const float *gs = smem + st * Cfg::STAGE_FLOATS + offg;
+        bwd_pass<Cfg, 0, Cfg::KA>(acc, gs, vb);
+        bwd_pass<Cfg, Cfg::KA, PW>(acc, gs, vb);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
+
+    if (s < x.NS) {
+      const int h = s * p.dpH + x.rp;
+      const int x0 = x.c0 + cgw * T;
+      const size_t HW = (size_t)p.H * p.W;
+      float *o = gin + ((size_t)x.n * p.C + x.cb * Cfg::CH_UNIT + cset * 64 + lj) * HW +
+                 (size_t)h * p.W + x0;
+#pragma unroll
+      for (int ci = 0; ci < Cfg::NCH; ++ci) {
+        if (x0 < p.W)
+          *reinterpret_cast<float4 *>(o + (size_t)ci * 8 * HW) =
+              make_float4(acc[0][ci], acc[1][ci], acc[2][ci], acc[3][ci]);
+        if (x0 + 4 < p.W)
+          *reinterpret_cast<float4 *>(o + (size_t)ci * 8 * HW + 4) =
+              make_float4(acc[4][ci], acc[5][ci], acc[6][ci], acc[7][ci]);
+      }
+    }
+  }
+}
+
+template <class Cfg>
+int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, int H, int W,
+               int dpH, cudaStream_t stream) {
+  BwdParams p;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.dpH = dpH;
+  p.NCT = (W + Cfg::COLS - 1) / Cfg::COLS;
+  p.NCB = C / Cfg::CH_UNIT;
+  int ng = 0;
+  for (int rp = 0; rp < dpH; ++rp) {
+    const int NS = b200::sublattice_rows(H, dpH, rp);
+    for (int s0 = 0; s0 < NS; s0 += b200::kRowsPerGroup) {
+      B200_CHECK(ng < b200::kSamplerMaxGroups, "sampler_fast_backward: too many row groups");
+      p.g.prefix[ng] = ng * p.NCT * p.NCB;
+      p.g.rp[ng] = (short)rp;
+      p.g.s0[ng] = (short)s0;
+      ++ng;
+    }
+  }
+  p.g.ngroups = ng;
+  p.g.units_per_sample = ng * p.NCT * p.NCB;
+  p.total_units = p.g.units_per_sample * B;
+  if (p.total_units == 0) return 0;
+
+  CUtensorMap map_o, map_g;
+  {
+    const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * C};
+    const uint64_t strides[3] = {4, (uint64_t)W * 4, (uint64_t)H * W * 4};
+    const uint32_t box[3] = {(uint32_t)Cfg::NC, 1, (uint32_t)Cfg::CH_UNIT};
+    if (int e = b200::make_tensor_map(&map_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, other, dims,
+                                      strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+      return e;
+  }
+  {
+    const uint64_t HW = (uint64_t)H * W;
+    const uint64_t dims[5] = {(uint64_t)W, (uint64_t)H, (uint64_t)Cfg::PW, (uint64_t)Cfg::PH, (uint64_t)B};
+    const uint64_t strides[5] = {4, (uint64_t)W * 4, HW * 4, HW * 4 * Cfg::PW, HW * 4 * Cfg::PW * Cfg::PH};
+    const uint32_t box1[5] = {(uint32_t)Cfg::GC, 1, (uint32_t)Cfg::PW, 1, 1};
+    const uint32_t box2[5] = {(uint32_t)Cfg::NC, 1, (uint32_t)Cfg::PW, 4, 1};
+    if (int e = b200::make_tensor_map(&map_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, gout, dims,
+                                      strides, Cfg::WHICH == 1 ? box1 : box2,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+      return e;
+  }
+  auto kern = sampler_bwd_kernel<Cfg>;
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int grid = p.total_units < b200::num_sms() ? p.total_units : b200::num_sms();
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(map_o, map_g, gin, p);
+  B200_LAUNCH_OK(Cfg::WHICH == 1 ? "sampler_bwd_kernel<gIn1>" : "sampler_bwd_kernel<gIn2>");
+  return 0;
+}
+
+}  // namespace
+
+namespace b200 {
+
+int sampler_fast_backward(const float *in1, const float *in2, const float *gout, float *gin1,
+                          float *gin2, int B, int C, int H, int W, const int *q,
+                          cudaStream_t stream) {
+  const int patchH = q[2], patchW = q[3], dpH = q[8], dpW = q[9];
+  if (patchH == 21 && patchW == 21 && dpW == 2) {
+    if (int e = launch_bwd<BwdCfg<21, 21, 2, 1>>(in2, gout, gin1, B, C, H, W, dpH, stream)) return e;
+    return launch_bwd<BwdCfg<21, 21, 2, 2>>(in1, gout, gin2, B, C, H, W, dpH, stream);
+  }
+  if (patchH == 9 && patchW == 9 && dpW == 1) {
+    if (int e = launch_bwd<BwdCfg<9, 9, 1, 1>>(in2, gout, gin1, B, C, H, W, dpH, stream)) return e;
+    return launch_bwd<BwdCfg<9, 9, 1, 2>>(in1, gout, gin2, B, C, H, W, dpH, stream);
+  }
+  set_error("sampler_fast_backward: no instantiation for patch %dx%d dilation_patch_w %d", patchH,
+            patchW, dpW);
+  return -1;
+}
+
+// The structure the register-blocked kernels cover (everything else runs on sampler_generic.cu).
+bool sampler_fast_applicable(int B, int C, int H, int W, const int *q, int dtype, int backward) {
+  (void)B;
+  if (dtype != B200CORR_F32) return false;
+  if (q[0] != 1 || q[1] != 1 || q[4] != 0 || q[5] != 0 || q[10] != 1 || q[11] != 1) return false;
+  const int patchH = q[2], patchW = q[3], dpH = q[8], dpW = q[9];
+  const bool shape = (patchH == 21 && patchW == 21 && dpW == 2) || (patchH == 9 && patchW == 9 && dpW == 1);
+  if (!shape) return false;
+  if (W % 4 != 0 || W < 4 || H < 1) return false;
+  if (dpH < 1 || dpH > 8) return false;
+  if ((long long)B * C >= (1ll << 31)) return false;
+  int ng = 0;
+  for (int rp = 0; rp < dpH; ++rp) ng += (sublattice_rows(H, dpH, rp) + kRowsPerGroup - 1) / kRowsPerGroup;
+  if (ng > kSamplerMaxGroups) return false;
+  if (backward) return C % 128 == 0;
+  return C % 8 == 0;
+}
+
+}  // namespace b200

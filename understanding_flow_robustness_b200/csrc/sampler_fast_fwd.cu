@@ -1,0 +1,316 @@
+// sampler_fast_fwd.cu -- register-blocked, TMA-staged forward of the spatial correlation sampler
+// for the FlowNetC / PWC-Net call-site structure (kernel_size 1, stride 1, padding 0):
+//
+//     out[n, ph, pw, h, w] = sum_c in1[n, c, h, w] * in2[n, c, h + (ph-RH)*dpH, w + (pw-RW)*dpW]
+//
+// Replaces correlation_cuda_forward + correlation_cuda_forward_kernel of the reference
+// (correlation_cuda_kernel.cu:22-83, 236-273: one 32-thread block per output pixel, 441 serial
+// displacements, thread-0 serial reduction, NHWC permute copies of both inputs).
+//
+// Design (DESIGN.md section "sampler forward"):
+//   * Row displacements are multiples of dpH, so rows split into dpH independent "parity classes";
+//     inside a class every displacement is a unit step on the sub-lattice of rows.  TMA loads only
+//     the rows of one class (tensor-map element stride dpH on the row axis) straight from NCHW --
+//     no layout copy -- and zero-fills everything outside the image, which IS the reference's
+//     WITHIN_BOUNDS rule (correlation.cpp:24,28) for this structure.
+//   * Work item = (pixel row s, column group g of 8 pixels, row displacement e).  One thread owns
+//     one item and keeps its 8 x PW accumulators (168 for FlowNetC) in registers for the whole
+//     channel loop: per channel it needs 8 in1 values and a window of 8+(PW-1)*dpW in2 values,
+//     i.e. 14 LDS.128 for 168 FFMA -- the Toeplitz reuse that lifts the loop off the
+//     shared-memory roof onto the FP32 pipe.
+//   * A warp is 4 pixel rows x 8 items: the 4 lanes of an item column share in2 addresses only
+//     through the hardware multicast of identical/neighbouring words and the 8 lanes of a pixel row
+//     share the in1 address, so one warp-wide LDS.128 touches few distinct 16-byte chunks.
+//   * Row displacements that fall outside the image for every row of a group are never computed
+//     (their output planes are zero-filled by the same threads), so the work tracks the in-bounds
+//     MAC count rather than the dense one.
+//   * Persistent CTAs (one per SM, 256 threads, <=255 registers), static round-robin over units; a
+//     3-stage mbarrier ring over 8-channel chunks that keeps running across unit boundaries.
+#include "sampler_fast.cuh"
+
+namespace {
+using namespace b200dev;
+
+constexpr int odd4(int x) {  // round up to a multiple of 4 floats whose 16-byte chunk count is odd
+  int c = (x + 3) / 4;
+  if (c % 2 == 0) ++c;
+  return 4 * c;
+}
+
+template <int PH_, int PW_, int DPW_>
+struct FwdCfg {
+  static constexpr int PH = PH_, PW = PW_, DPW = DPW_;
+  static constexpr int T = 8;                          // pixels per thread
+  static constexpr int RH = (PH - 1) / 2, RW = (PW - 1) / 2;
+  static constexpr int HALO = RW * DPW;
+  static constexpr int WIN = T + (PW - 1) * DPW;       // in2 window of one thread, floats
+  static_assert(WIN % 4 == 0, "window must be a whole number of 16-byte chunks");
+  static constexpr int GMAX = 5;                       // column groups one unit may span
+  static constexpr int NRB = b200::kRowsPerGroup + PH - 1;  // in2 rows staged per unit
+  static constexpr int NC1 = odd4(GMAX * T);
+  static constexpr int NC2 = odd4(GMAX * T + (PW - 1) * DPW);
+  static constexpr int CC = 8;                         // channels per pipeline stage
+  static constexpr int NST = 3;                        // pipeline stages
+  static constexpr int IN2_FLOATS = CC * NRB * NC2;
+  static constexpr int IN1_FLOATS = CC * b200::kRowsPerGroup * NC1;
+  static constexpr int STAGE_FLOATS = IN2_FLOATS + IN1_FLOATS;
+  static constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
+  static_assert((IN2_FLOATS * 4) % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA destination alignment");
+  static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 128;
+  static constexpr int SLOTS = 64;                     // items per unit (8 warps x 8)
+};
+
+struct FwdParams {
+  int B, C, H, W, dpH, NG, total_units;
+  b200::SamplerGroups g;
+};
+
+// Displacement range and unit split of one row group (same arithmetic on host and device).
+__host__ __device__ inline void fwd_group_geom(int NS, int s0, int RH, int NG, int GMAX, int SLOTS,
+                                               int &e_lo, int &ne, int &nch, int &cs) {
+  const int s_last = (s0 + b200::kRowsPerGroup - 1 < NS - 1) ? s0 + b200::kRowsPerGroup - 1 : NS - 1;
+  e_lo = -RH > -s_last ? -RH : -s_last;
+  const int e_hi = RH < NS - 1 - s0 ? RH : NS - 1 - s0;
+  ne = e_hi - e_lo + 1;
+  const int nitems = NG * ne;
+  int cap = (GMAX - 1) * ne;
+  if (cap > SLOTS) cap = SLOTS;
+  nch = (nitems + cap - 1) / cap;
+  cs = (nitems + nch - 1) / nch;
+}
+
+struct Unit {
+  int n, rp, s0, NS, e_lo, ne, item0, cnt, g0;
+};
+
+template <class Cfg>
+__device__ __forceinline__ void decode_unit(const FwdParams &p, int u, Unit &x) {
+  x.n = u / p.g.units_per_sample;
+  const int r = u - x.n * p.g.units_per_sample;
+  int gi = 0;
+  while (gi + 1 < p.g.ngroups && p.g.prefix[gi + 1] <= r) ++gi;
+  x.rp = p.g.rp[gi];
+  x.s0 = p.g.s0[gi];
+  x.NS = (p.H - x.rp + p.dpH - 1) / p.dpH;
+  int nch, cs;
+  fwd_group_geom(x.NS, x.s0, Cfg::RH, p.NG, Cfg::GMAX, Cfg::SLOTS, x.e_lo, x.ne, nch, cs);
+  const int k = r - p.g.prefix[gi];
+  x.item0 = k * cs;
+  const int nitems = p.NG * x.ne;
+  x.cnt = nitems - x.item0 < cs ? nitems - x.item0 : cs;
+  x.g0 = x.item0 / x.ne;
+}
+
+__device__ __forceinline__ void stg128(float *p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(256, 1)
+sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+                   float *__restrict__ out, const FwdParams p) {
+  constexpr int PH = Cfg::PH, PW = Cfg::PW, DPW = Cfg::DPW, CC = Cfg::CC, NST = Cfg::NST;
+  constexpr int NC1 = Cfg::NC1, NC2 = Cfg::NC2, NRB = Cfg::NRB;
+  extern __shared__ __align__(128) float smem[];  // NST stages, then the mbarriers
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + NST * Cfg::STAGE_FLOATS);
+  uint64_t *empty_bar = full_bar + NST;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int li = lane >> 3;  // pixel row inside the group (0..3)
+  const int lj = lane & 7;   // item column inside the warp (0..7)
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map1);
+    tma_prefetch_desc(&map2);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 8);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int nunits = p.total_units;
+  const int cpu = p.C / CC;  // channel chunks per unit
+
+  // ---- producer state (thread 0 only): the load stream runs NST-1 chunks ahead of the math
+  int pu = blockIdx.x, pc = 0;
+  uint32_t pq = 0;
+  Unit px;
+  if (tid == 0 && pu < nunits) decode_unit<Cfg>(p, pu, px);
+  auto issue = [&]() {
+    if (pu >= nunits) return;
+    const int st = pq % NST;
+    float *dst = smem + st * Cfg::STAGE_FLOATS;
+    mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
+    const int ch = px.n * p.C + pc * CC;
+    tma_load_3d(dst, &map2, &full_bar[st], px.g0 * Cfg::T - Cfg::HALO,
+                (px.s0 + px.e_lo) * p.dpH + px.rp, ch);
+    tma_load_3d(dst + Cfg::IN2_FLOATS, &map1, &full_bar[st], px.g0 * Cfg::T,
+                px.s0 * p.dpH + px.rp, ch);
+    ++pq;
+    if (++pc == cpu) {
+      pc = 0;
+      pu += gridDim.x;
+      if (pu < nunits) decode_unit<Cfg>(p, pu, px);
+    }
+  };
+  if (tid == 0)
+    for (int s = 0; s < NST - 1; ++s) issue();
+
+  uint32_t q = 0;  // chunks consumed so far by this CTA
+  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    Unit x;
+    decode_unit<Cfg>(p, u, x);
+    const int slot = warp * 8 + lj;
+    const bool active = slot < x.cnt;
+    const int item = x.item0 + (active ? slot : 0);
+    const int g = item / x.ne;
+    const int e = x.e_lo + (item - g * x.ne);
+    const int s = x.s0 + li;
+    const int rbox = li + (e - x.e_lo);        // in2 row inside the staged box
+    const int cb = (g - x.g0) * Cfg::T;        // column offset inside both boxes
+    const int off2 = rbox * NC2 + cb;
+    const int off1 = Cfg::IN2_FLOATS + li * NC1 + cb;
+
+    float acc[Cfg::T][PW];
+#pragma unroll
+    for (int t = 0; t < Cfg::T; ++t)
+#pragma unroll
+      for (int k = 0; k < PW; ++k) acc[t][k] = 0.f;
+
+    for (int c = 0; c < cpu; ++c, ++q) {
+      const int st = q % NST;
+      if (tid == 0) {
+        if (q > 0) mbar_wait(&empty_bar[(q - 1) % NST], ((q - 1) / NST) & 1);
+        issue();
+      }
+      mbar_wait(&full_bar[st], (q / NST) & 1);
+      const float *sb = smem + st * Cfg::STAGE_FLOATS + off2;
+      const float *sa = smem + st * Cfg::STAGE_FLOATS + off1;
+#pragma unroll 2
+      for (int cc = 0; cc < CC; ++cc) {
+        const float4 a0 = lds128(sa + cc * b200::kRowsPerGroup * NC1);
+        const float4 a1 = lds128(sa + cc * b200::kRowsPerGroup * NC1 + 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int sgm = 0; sgm < Cfg::WIN / 4; ++sgm) {
+          const float4 v4 = lds128(sb + cc * NRB * NC2 + 4 * sgm);
+          const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int uu = 0; uu < 4; ++uu) {
+#pragma unroll
+            for (int t = 0; t < Cfg::T; ++t) {
+              const int d = 4 * sgm + uu - t;  // = k * DPW
+              if (d >= 0 && d % DPW == 0 && d / DPW < PW)
+                acc[t][d / DPW] = fmaf(a[t], v[uu], acc[t][d / DPW]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
+
+    // ---- epilogue: every (n, ph, pw, h, w) of this unit's rows/columns is written exactly once
+    if (active && s < x.NS) {
+      const size_t HW = (size_t)p.H * p.W;
+      const int h = s * p.dpH + x.rp;
+      const int w0 = g * Cfg::T;
+      const bool lo_ok = w0 < p.W, hi_ok = w0 + 4 < p.W;
+      float *o = out + (((size_t)x.n * PH + (e + Cfg::RH)) * PW) * HW + (size_t)h * p.W + w0;
+#pragma unroll
+      for (int k = 0; k < PW; ++k) {
+        if (lo_ok) stg128(o + k * HW, acc[0][k], acc[1][k], acc[2][k], acc[3][k]);
+        if (hi_ok) stg128(o + k * HW + 4, acc[4][k], acc[5][k], acc[6][k], acc[7][k]);
+      }
+      // row displacements clipped away for the whole group: zero planes
+      const int nclip = PH - x.ne;
+      const int below = x.e_lo + Cfg::RH;  // clipped planes [0, below) and [below + ne, PH)
+      for (int qq = e - x.e_lo; qq < nclip; qq += x.ne) {
+        const int phc = qq < below ? qq : qq + x.ne;
+        float *z = out + (((size_t)x.n * PH + phc) * PW) * HW + (size_t)h * p.W + w0;
+        for (int k = 0; k < PW; ++k) {
+          if (lo_ok) stg128(z + k * HW, 0.f, 0.f, 0.f, 0.f);
+          if (hi_ok) stg128(z + k * HW + 4, 0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  }
+}
+
+template <class Cfg>
+int launch_fwd(const float *in1, const float *in2, float *out, int B, int C, int H, int W, int dpH,
+               cudaStream_t stream) {
+  FwdParams p;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.dpH = dpH;
+  p.NG = (W + Cfg::T - 1) / Cfg::T;
+  int ng = 0, units = 0;
+  for (int rp = 0; rp < dpH; ++rp) {
+    const int NS = b200::sublattice_rows(H, dpH, rp);
+    for (int s0 = 0; s0 < NS; s0 += b200::kRowsPerGroup) {
+      B200_CHECK(ng < b200::kSamplerMaxGroups, "sampler_fast_forward: too many row groups");
+      int e_lo, ne, nch, cs;
+      fwd_group_geom(NS, s0, Cfg::RH, p.NG, Cfg::GMAX, Cfg::SLOTS, e_lo, ne, nch, cs);
+      p.g.prefix[ng] = units;
+      p.g.rp[ng] = (short)rp;
+      p.g.s0[ng] = (short)s0;
+      units += nch;
+      ++ng;
+    }
+  }
+  p.g.prefix[ng] = units;
+  p.g.ngroups = ng;
+  p.g.units_per_sample = units;
+  p.total_units = units * B;
+  if (p.total_units == 0) return 0;
+
+  CUtensorMap map1, map2;
+  const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * C};
+  const uint64_t strides[3] = {4, (uint64_t)W * 4, (uint64_t)H * W * 4};
+  const uint32_t estr[3] = {1, (uint32_t)dpH, 1};
+  const uint32_t box2[3] = {(uint32_t)Cfg::NC2, (uint32_t)((Cfg::NRB - 1) * dpH + 1), (uint32_t)Cfg::CC};
+  const uint32_t box1[3] = {(uint32_t)Cfg::NC1, (uint32_t)((b200::kRowsPerGroup - 1) * dpH + 1),
+                            (uint32_t)Cfg::CC};
+  if (int e = b200::make_tensor_map(&map2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, in2, dims, strides,
+                                    box2, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, estr))
+    return e;
+  if (int e = b200::make_tensor_map(&map1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, in1, dims, strides,
+                                    box1, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, estr))
+    return e;
+
+  auto kern = sampler_fwd_kernel<Cfg>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int grid = p.total_units < b200::num_sms() ? p.total_units : b200::num_sms();
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(map1, map2, out, p);
+  B200_LAUNCH_OK("sampler_fwd_kernel");
+  return 0;
+}
+
+}  // namespace
+
+namespace b200 {
+
+bool sampler_fast_fwd_shape_ok(int patchH, int patchW, int dpW) {
+  return (patchH == 21 && patchW == 21 && dpW == 2) || (patchH == 9 && patchW == 9 && dpW == 1);
+}
+
+int sampler_fast_forward(const float *in1, const float *in2, float *out, int B, int C, int H, int W,
+                         const int *q, cudaStream_t stream) {
+  const int patchH = q[2], patchW = q[3], dpH = q[8], dpW = q[9];
+  if (patchH == 21 && patchW == 21 && dpW == 2)
+    return launch_fwd<FwdCfg<21, 21, 2>>(in1, in2, out, B, C, H, W, dpH, stream);
+  if (patchH == 9 && patchW == 9 && dpW == 1)
+    return launch_fwd<FwdCfg<9, 9, 1>>(in1, in2, out, B, C, H, W, dpH, stream);
+  set_error("sampler_fast_forward: no instantiation for patch %dx%d dilation_patch_w %d", patchH,
+            patchW, dpW);
+  return -1;
+}
+
+}  // namespace b200
