@@ -52,7 +52,8 @@ extern "C" {
 
 /* precision of the all-pairs contraction */
 #define B200CORR_PREC_TF32 0   /* one tcgen05 kind::tf32 pass, inputs rounded to TF32 (rna)      */
-#define B200CORR_PREC_TF32X3 1 /* 3-pass split-TF32 (hi*hi + hi*lo + lo*hi), ~fp32 accuracy      */
+#define B200CORR_PREC_TF32X3 1 /* reserved: 3-pass split-TF32; not implemented, returns an error */
+#define B200CORR_PREC_FP32 2   /* exact fp32 FMA accumulation on the CUDA cores (SIMT tile GEMM) */
 
 /* coordinate arithmetic of the lookup */
 #define B200CORR_LOOKUP_GRIDSAMPLE 0 /* reproduce utils.py:65-70 + grid_sample's un-normalise     */

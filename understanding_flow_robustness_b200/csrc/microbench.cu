@@ -9,16 +9,22 @@
 namespace {
 
 __device__ __forceinline__ int lds_pattern_chunk(int pattern, int lane) {
+  const int li = lane >> 3, lj = lane & 7;
   switch (pattern) {
     case 0: return lane;                    // 32 distinct 16-B chunks (512 B)
     case 1: return lane >> 2;               // 8 distinct, 4 consecutive lanes share
-    case 2: return lane & 7;                // 8 distinct, lanes l, l+8, l+16, l+24 share
-    case 3: return lane >> 3;               // 4 distinct
+    case 2: return lane & 7;                // 8 distinct, every quarter-warp reads all 8 (bwd v-load)
+    case 3: return (lane >> 3) * 9;         // 4 distinct, one per quarter-warp (bwd G-load)
     case 4: return 0;                       // 1 distinct (full broadcast)
-    case 5: return (lane & 7) * 21;         // 8 distinct rows, row stride 84 floats (= 21 chunks)
-    case 6: return (lane >> 2) * 21;        // 8 distinct rows, consecutive lanes share
-    case 7: return (lane % 11) * 21;        // 11 distinct rows (176 B)
-    case 8: return (lane & 15);             // 16 distinct
+    case 5: return (lane & 3) + 4 * (lane >> 4);  // 4 distinct per half-warp, halves differ
+    case 6: return (li + lj) * 21;          // fwd in2 load as first written: 11 distinct rows
+    case 7: {                               // fwd in2 load remapped: 7 distinct rows per half-warp
+      const int i = (lane >> 2) & 3, j = (lane & 3) + 4 * (lane >> 4);
+      return (i + j) * 21;
+    }
+    case 8: return lane & 15;               // 16 distinct, halves identical
+    case 9: return (lane & 3) * 21;         // 4 distinct rows, every quarter identical
+    case 10: return (lane >> 1);            // 16 distinct, pairs share
     default: return lane;
   }
 }
@@ -26,30 +32,31 @@ __device__ __forceinline__ int lds_pattern_chunk(int pattern, int lane) {
 __global__ void __launch_bounds__(512) lds_probe_kernel(float *sink, int iters, int pattern,
                                                         unsigned long long *cycles) {
   extern __shared__ float4 sm4[];
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x)
     sm4[i] = make_float4((float)i, 1.f, 2.f, 3.f);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t base =
-      b200dev::smem_u32(sm4) + 16u * (uint32_t)(lds_pattern_chunk(pattern, lane) + (warp & 3) * 256);
-  float a0 = 0.f, a1 = 0.f;
+      b200dev::smem_u32(sm4) + 16u * (uint32_t)(lds_pattern_chunk(pattern, lane) + (warp & 7) * 256);
+  uint32_t a0 = 0;
   unsigned long long t0 = clock64();
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      float x, y, z, w;
-      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                   : "=f"(x), "=f"(y), "=f"(z), "=f"(w)
-                   : "r"(base + (uint32_t)(u & 1) * 16u * 1024u));
-      a0 += x;
-      a1 += w;
+      uint32_t x, y, z, w;
+      // distinct immediate offset per unrolled load + memory clobber: nothing can be folded
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(x), "=r"(y), "=r"(z), "=r"(w)
+                   : "r"(base + (uint32_t)u * 2048u)
+                   : "memory");
+      a0 ^= x ^ y ^ z ^ w;
     }
   }
   unsigned long long t1 = clock64();
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
-  if (a0 + a1 == 123.456f) sink[0] = a0;
+  if (a0 == 0x12345u) sink[0] = (float)a0;
 }
 
 // 8 x 21 Toeplitz register update, operands refreshed from registers only.
@@ -97,7 +104,8 @@ int b200corr_probe_lds(int pattern, int warps, int iters, float *cycles_per_lds,
   unsigned long long *cyc = nullptr;
   B200_CUDA(cudaMalloc(&sink, sizeof(float)));
   B200_CUDA(cudaMalloc(&cyc, sizeof(unsigned long long) * blocks));
-  const size_t smem = 2048 * sizeof(float4);
+  const size_t smem = 4096 * sizeof(float4);
+  B200_CUDA(cudaFuncSetAttribute(lds_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   lds_probe_kernel<<<blocks, warps * 32, smem, stream>>>(sink, 4, pattern, cyc);
   lds_probe_kernel<<<blocks, warps * 32, smem, stream>>>(sink, iters, pattern, cyc);
   B200_LAUNCH_OK("lds_probe_kernel");

@@ -1,0 +1,450 @@
+// raft_allpairs.cu -- RAFT all-pairs correlation volume + average-pool pyramid.
+//
+// Replaces CorrBlock.__init__ / CorrBlock.corr of the reference (models/raft/corr.py:55-64,98-106):
+//     vol0[b, p1, p2] = (1/sqrt(C)) * sum_c f1[b,c,p1] * f2[b,c,p2]        (torch.matmul + divide)
+//     vol_{l+1}       = avg_pool2d(vol_l, 2, stride 2) over p2 = (y, x)     (3 more passes)
+// which costs one cuBLAS SGEMM plus four elementwise passes over a 236 MB/sample volume.
+//
+// Here (precision TF32, the default):
+//   1. prep kernel: NCHW fp32 features -> [B][HW][Cp] (K-major) rounded to TF32 (cvt.rna), Cp = C
+//      rounded up to 32, zero padded.  7.9 MB/sample per map -- noise next to the volume.
+//   2. one persistent tcgen05 kernel.  CTA tile = 128 query pixels (M) x one 8x32 spatial patch of
+//      key pixels (N = 256), K = Cp in blocks of 32 TF32 (128-byte swizzled rows).
+//        warp 0   : TMA producer (A: [Cp,HW,B] box 32x128; B: [Cp,W,H,B] box 32x32x8), 3-stage ring
+//        warp 1   : tcgen05.mma.kind::tf32 issuer (M128 N256 K8, 4 per k-block), accumulators in
+//                   TMEM, double buffered (2 x 256 columns) so the epilogue of tile i overlaps the
+//                   MMAs of tile i+1
+//        warp 2   : TMEM allocator
+//        warps 4-7: epilogue.  Each thread owns one query row = a full 8x32 patch of keys, so the
+//                   2x2, 4x4 and 8x8 average pools are register-local.  Level 0 goes
+//                   TMEM -> regs -> swizzled smem -> TMA store (whole 128-byte lines); levels 1-3 are
+//                   written straight from registers (64/32/16-byte runs).
+//      The volume is written exactly once and never re-read: 313 MB/sample instead of ~1.1 GB.
+//   Precision FP32 (exact, also the path for W % 4 != 0): a plain SIMT tile GEMM + pooling kernels.
+//
+// Error bound of the TF32 path (documented in DESIGN.md, asserted in tests): inputs are rounded to
+// 11 significant bits (rel. error <= 2^-11 each), products accumulate in fp32, so
+//     |vol - exact| <= (2^-10 + 2^-22) * scale * sum_c |f1_c * f2_c|  (+ fp32 accumulation error).
+#include "tcgen05.cuh"
+
+namespace {
+using namespace b200dev;
+
+// ------------------------------------------------------------------------------ prep (transpose)
+// in [B][C][HW] -> out [B][HW][Cp], tf32-rounded, channels >= C zero
+__global__ void __launch_bounds__(256)
+prep_kmajor_tf32_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int Cp, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, p = p0 + tx;
+    float v = 0.f;
+    if (c < C && p < HW) v = in[((size_t)b * C + c) * HW + p];
+    tile[ty + 8 * i][tx] = to_tf32_rna(v);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = p0 + ty + 8 * i, c = c0 + tx;
+    if (p < HW && c < Cp) out[((size_t)b * HW + p) * Cp + c] = tile[tx][ty + 8 * i];
+  }
+}
+
+// ------------------------------------------------------------------------------ tcgen05 kernel
+namespace tc {
+constexpr int BM = 128, BN = 256, BK = 32;
+constexpr int PH = 8, PW = 32;  // key patch
+constexpr int NST = 3;
+constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_ROW_BYTES = 32 * 128;                 // one TMA store box: 32 query rows x 32 floats
+constexpr int EPI_WARP_BYTES = 2 * 2 * EPI_ROW_BYTES;   // [double buffer][2 patch rows]
+constexpr int SMEM_BYTES = NST * STAGE_BYTES + 4 * EPI_WARP_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 512;
+
+struct Params {
+  int B, HW, H, W, KB;       // KB = Cp / 32
+  int MT, NTY, NTX;          // tile counts
+  float scale;
+  float *lvl[3];             // levels 1..3 (nullptr if not requested)
+  int LH[3], LW[3];
+};
+}  // namespace tc
+
+// N consecutive floats starting at column x of a row of width WL
+template <int N>
+__device__ __forceinline__ void store_row_vec(float *dst, const float (&v)[N], int x, int WL,
+                                              bool vec_ok) {
+  if (vec_ok) {
+#pragma unroll
+    for (int j = 0; j < N; j += 4)
+      if (x + j < WL) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (x + j < WL) dst[j] = v[j];
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const __grid_constant__ CUtensorMap mapC, const tc::Params p) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128-byte swizzle atoms
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - raw);
+  uint8_t *epi = sm + NST * STAGE_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(epi + 4 * EPI_WARP_BYTES);
+  uint64_t *full_bar = bars, *empty_bar = bars + NST;
+  uint64_t *tfull_bar = bars + 2 * NST, *tempty_bar = bars + 2 * NST + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapC);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int NT = p.NTY * p.NTX;
+  const int total = p.B * p.MT * NT;
+
+  if (warp == 0) {
+    // ================= TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nt = t % NT, mt = (t / NT) % p.MT, b = t / (NT * p.MT);
+        const int y0 = (nt / p.NTX) * PH, x0 = (nt % p.NTX) * PW, m0 = mt * BM;
+        for (int kb = 0; kb < p.KB; ++kb, ++it) {
+          const int st = it % NST;
+          mbar_wait(&empty_bar[st], ((it / NST) & 1) ^ 1);
+          uint8_t *a = sm + st * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[st], STAGE_BYTES);
+          tma_load_3d(a, &mapA, &full_bar[st], kb * BK, m0, b);
+          tma_load_4d(a + A_BYTES, &mapB, &full_bar[st], kb * BK, x0, y0, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&tempty_bar[buf], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < p.KB; ++kb, ++it) {
+          const int st = it % NST;
+          mbar_wait(&full_bar[st], (it / NST) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = base + st * STAGE_BYTES;
+          const uint64_t adesc = umma_desc_kmajor_sw128(a_addr);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + A_BYTES);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)  // 8 tf32 = 32 bytes per MMA: +2 in the 16-byte address field
+            umma_tf32(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
+          umma_commit(&empty_bar[st]);
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (warp w may only touch TMEM lanes 32*(w%4) .. +31)
+    const int wq = warp & 3;
+    uint8_t *ebuf = epi + wq * EPI_WARP_BYTES;
+    const bool v1 = p.lvl[0] && (p.LW[0] % 4 == 0), v2 = p.lvl[1] && (p.LW[1] % 4 == 0),
+               v3 = p.lvl[2] && (p.LW[2] % 4 == 0);
+    uint32_t lt = 0, sbuf = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+      const int nt = t % NT, mt = (t / NT) % p.MT, b = t / (NT * p.MT);
+      const int y0 = (nt / p.NTX) * PH, x0 = (nt % p.NTX) * PW;
+      const int mrow0 = mt * BM + wq * 32;
+      const int m = mrow0 + lane;
+      const bool m_ok = m < p.HW;
+      const size_t q = (size_t)b * p.HW + (m_ok ? m : 0);
+      const int buf = lt & 1;
+      mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(wq * 32) << 16);
+
+      float p1prev[16], p2prev[8];
+#pragma unroll
+      for (int step = 0; step < 4; ++step, sbuf ^= 1) {
+        float r0[32], r1[32];
+        tmem_ld_32x32(taddr + step * 64, r0);
+        tmem_ld_32x32(taddr + step * 64 + 32, r1);
+        // the staging buffer written two steps ago must have been read by its TMA stores
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          r0[i] *= p.scale;
+          r1[i] *= p.scale;
+        }
+        // ---- level 0: two patch rows -> swizzled staging -> TMA store
+        uint8_t *s0 = ebuf + sbuf * (2 * EPI_ROW_BYTES);
+        uint8_t *s1 = s0 + EPI_ROW_BYTES;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int off = lane * 128 + ((j ^ (lane & 7)) << 4);
+          *reinterpret_cast<float4 *>(s0 + off) = make_float4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
+          *reinterpret_cast<float4 *>(s1 + off) = make_float4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&mapC, s0, x0, y0 + 2 * step, mrow0, b);
+          tma_store_4d(&mapC, s1, x0, y0 + 2 * step + 1, mrow0, b);
+          tma_store_commit();
+        }
+        // ---- level 1: 2x2 means of the two rows -> 16 values
+        float p1[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          p1[j] = (((r0[2 * j] + r0[2 * j + 1]) + r1[2 * j]) + r1[2 * j + 1]) * 0.25f;
+        if (p.lvl[0] && m_ok) {
+          const int y1 = y0 / 2 + step, x1 = x0 / 2;
+          if (y1 < p.LH[0])
+            store_row_vec(p.lvl[0] + (q * p.LH[0] + y1) * p.LW[0] + x1, p1, x1, p.LW[0], v1);
+        }
+        if (step & 1) {
+          // ---- level 2: means of two level-1 rows -> 8 values
+          float p2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            p2[j] = (((p1prev[2 * j] + p1prev[2 * j + 1]) + p1[2 * j]) + p1[2 * j + 1]) * 0.25f;
+          if (p.lvl[1] && m_ok) {
+            const int y2 = y0 / 4 + (step >> 1), x2 = x0 / 4;
+            if (y2 < p.LH[1])
+              store_row_vec(p.lvl[1] + (q * p.LH[1] + y2) * p.LW[1] + x2, p2, x2, p.LW[1], v2);
+          }
+          if (step == 3) {
+            float p3[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              p3[j] = (((p2prev[2 * j] + p2prev[2 * j + 1]) + p2[2 * j]) + p2[2 * j + 1]) * 0.25f;
+            if (p.lvl[2] && m_ok) {
+              const int y3 = y0 / 8, x3 = x0 / 8;
+              if (y3 < p.LH[2])
+                store_row_vec(p.lvl[2] + (q * p.LH[2] + y3) * p.LW[2] + x3, p3, x3, p.LW[2], v3);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p2prev[j] = p2[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) p1prev[j] = p1[j];
+        }
+      }
+      // all TMEM reads of this accumulator buffer are done: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------ exact fp32 path
+// vol0[b, m, n] = scale * sum_c f1[b,c,m] * f2[b,c,n]; 64x64 tile, 256 threads, 4x4 per thread
+__global__ void __launch_bounds__(256)
+allpairs_simt_kernel(const float *__restrict__ f1, const float *__restrict__ f2, float *__restrict__ vol,
+                     int C, int HW, float scale) {
+  __shared__ float As[16][64], Bs[16][64];
+  const int b = blockIdx.z, m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  const float *a = f1 + (size_t)b * C * HW, *bb = f2 + (size_t)b * C * HW;
+  for (int c0 = 0; c0 < C; c0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int k = i >> 6, j = i & 63;
+      As[k][j] = (c0 + k < C && m0 + j < HW) ? a[(size_t)(c0 + k) * HW + m0 + j] : 0.f;
+      Bs[k][j] = (c0 + k < C && n0 + j < HW) ? bb[(size_t)(c0 + k) * HW + n0 + j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 av = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= HW) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < HW) vol[((size_t)b * HW + m) * HW + n] = acc[i][j] * scale;
+    }
+  }
+}
+
+// out[q, y, x] = mean of the 2x2 block of in[q, 2y.., 2x..] (floor mode), q = flattened leading dims
+__global__ void __launch_bounds__(256)
+avgpool2_kernel(const float *__restrict__ in, float *__restrict__ out, long long Q, int Hi, int Wi) {
+  const int Ho = Hi / 2, Wo = Wi / 2;
+  const long long total = Q * Ho * Wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wo);
+    const long long t = i / Wo;
+    const int y = (int)(t % Ho);
+    const long long q = t / Ho;
+    const float *s = in + (q * Hi + 2 * y) * Wi + 2 * x;
+    out[i] = (((s[0] + s[1]) + s[Wi]) + s[Wi + 1]) * 0.25f;
+  }
+}
+
+int launch_pool(const float *in, float *out, long long Q, int Hi, int Wi, cudaStream_t stream) {
+  const long long total = Q * (Hi / 2) * (Wi / 2);
+  if (total == 0) return 0;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)b200::num_sms() * 16;
+  avgpool2_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, stream>>>(in, out, Q, Hi, Wi);
+  B200_LAUNCH_OK("avgpool2_kernel");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t b200corr_allpairs_workspace_bytes(int B, int C, int H, int W, int precision) {
+  if (precision == B200CORR_PREC_FP32) return 0;
+  const size_t Cp = (size_t)(C + 31) / 32 * 32;
+  return 2 * (size_t)B * H * W * Cp * sizeof(float);
+}
+
+int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_levels,
+                              int num_levels, int B, int C, int H, int W, float scale,
+                              int precision, void *workspace, size_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK(num_levels >= 1 && num_levels <= 8, "allpairs_pyramid: num_levels must be in [1, 8]");
+  B200_CHECK(B >= 0 && C >= 1 && H >= 1 && W >= 1, "allpairs_pyramid: bad sizes");
+  B200_CHECK(precision == B200CORR_PREC_TF32 || precision == B200CORR_PREC_FP32,
+             "allpairs_pyramid: precision %d not available (TF32 = 0, FP32 = 2)", precision);
+  if (B == 0) return 0;
+  B200_CHECK(f1 && f2 && h_levels && h_levels[0], "allpairs_pyramid: null pointer");
+  const int HW = H * W;
+  int LH[8], LW[8];
+  LH[0] = H; LW[0] = W;
+  for (int l = 1; l < num_levels; ++l) {
+    LH[l] = LH[l - 1] / 2;
+    LW[l] = LW[l - 1] / 2;
+    B200_CHECK(h_levels[l] || LH[l] * LW[l] == 0, "allpairs_pyramid: null level %d", l);
+  }
+  const long long Q = (long long)B * HW;
+  int first_unpooled = 1;  // first level that still has to be produced by the pooling kernel
+
+  if (precision == B200CORR_PREC_FP32 || W % 4 != 0) {
+    dim3 grid((HW + 63) / 64, (HW + 63) / 64, B);
+    allpairs_simt_kernel<<<grid, 256, 0, stream>>>(f1, f2, h_levels[0], C, HW, scale);
+    B200_LAUNCH_OK("allpairs_simt_kernel");
+  } else {
+    const int Cp = (C + 31) / 32 * 32;
+    const size_t need = 2 * (size_t)B * HW * Cp * sizeof(float);
+    B200_CHECK(workspace && workspace_bytes >= need,
+               "allpairs_pyramid: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    B200_CHECK(((uintptr_t)workspace & 127) == 0 && ((uintptr_t)h_levels[0] & 15) == 0,
+               "allpairs_pyramid: workspace must be 128-byte and level 0 16-byte aligned");
+    float *f1t = (float *)workspace, *f2t = f1t + (size_t)B * HW * Cp;
+    dim3 pgrid((HW + 31) / 32, Cp / 32, B);
+    prep_kmajor_tf32_kernel<<<pgrid, 256, 0, stream>>>(f1, f1t, C, Cp, HW);
+    B200_LAUNCH_OK("prep_kmajor_tf32_kernel");
+    prep_kmajor_tf32_kernel<<<pgrid, 256, 0, stream>>>(f2, f2t, C, Cp, HW);
+    B200_LAUNCH_OK("prep_kmajor_tf32_kernel");
+
+    CUtensorMap mapA, mapB, mapC;
+    {
+      const uint64_t dims[3] = {(uint64_t)Cp, (uint64_t)HW, (uint64_t)B};
+      const uint64_t str[3] = {4, (uint64_t)Cp * 4, (uint64_t)HW * Cp * 4};
+      const uint32_t box[3] = {tc::BK, tc::BM, 1};
+      if (int e = b200::make_tensor_map(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, f1t, dims, str, box,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+        return e;
+    }
+    {
+      const uint64_t dims[4] = {(uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      const uint64_t str[4] = {4, (uint64_t)Cp * 4, (uint64_t)W * Cp * 4, (uint64_t)HW * Cp * 4};
+      const uint32_t box[4] = {tc::BK, tc::PW, tc::PH, 1};
+      if (int e = b200::make_tensor_map(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, f2t, dims, str, box,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+        return e;
+    }
+    {
+      const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)HW, (uint64_t)B};
+      const uint64_t str[4] = {4, (uint64_t)W * 4, (uint64_t)HW * 4, (uint64_t)HW * HW * 4};
+      const uint32_t box[4] = {tc::PW, 1, 32, 1};
+      if (int e = b200::make_tensor_map(&mapC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, h_levels[0], dims, str,
+                                        box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE))
+        return e;
+    }
+    tc::Params p;
+    p.B = B; p.HW = HW; p.H = H; p.W = W; p.KB = Cp / 32;
+    p.MT = (HW + tc::BM - 1) / tc::BM;
+    p.NTY = (H + tc::PH - 1) / tc::PH;
+    p.NTX = (W + tc::PW - 1) / tc::PW;
+    p.scale = scale;
+    for (int l = 0; l < 3; ++l) {
+      const bool want = l + 1 < num_levels && LH[l + 1] * LW[l + 1] > 0;
+      p.lvl[l] = want ? h_levels[l + 1] : nullptr;
+      p.LH[l] = want ? LH[l + 1] : 0;
+      p.LW[l] = want ? LW[l + 1] : 0;
+      if (want) B200_CHECK(((uintptr_t)h_levels[l + 1] & 15) == 0, "allpairs_pyramid: level %d misaligned", l + 1);
+    }
+    first_unpooled = 4;
+    B200_CUDA(cudaFuncSetAttribute(allpairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   tc::SMEM_BYTES));
+    const int total = B * p.MT * p.NTY * p.NTX;
+    const int grid = total < b200::num_sms() ? total : b200::num_sms();
+    allpairs_tc_kernel<<<grid, 256, tc::SMEM_BYTES, stream>>>(mapA, mapB, mapC, p);
+    B200_LAUNCH_OK("allpairs_tc_kernel");
+  }
+  for (int l = first_unpooled; l < num_levels; ++l)
+    if (LH[l] * LW[l] > 0)
+      if (int e = launch_pool(h_levels[l - 1], h_levels[l], Q, LH[l - 1], LW[l - 1], stream)) return e;
+  return 0;
+}
+
+}  // extern "C"

@@ -51,8 +51,8 @@ struct BwdCfg {
   static constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
   static_assert((OTHER_FLOATS * 4) % 128 == 0 && STAGE_BYTES % 128 == 0 && (GLI * 4) % 128 == 0,
                 "TMA destination alignment");
-  static constexpr int NST = (4 * STAGE_BYTES + 128 <= 227 * 1024) ? 4 : 3;
-  static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 128;
+  static constexpr int NST = (4 * STAGE_BYTES + 256 <= 227 * 1024) ? 4 : 3;
+  static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 256;
   static constexpr int KA = (PW + 1) / 2;             // first k' pass: [0, KA), second: [KA, PW)
 };
 
@@ -86,35 +86,31 @@ __device__ __forceinline__ void decode_bunit(const BwdParams &p, int u, BUnit &x
 
 // One k' pass [K0, K1): coefficients to registers, then stream the `other` window per channel.
 template <class Cfg, int K0, int K1>
-__device__ __forceinline__ void bwd_pass(float (&acc)[Cfg::T][Cfg::NCH], const float *gs,
+__device__ __forceinline__ void bwd_pass(float2 (&acc2)[Cfg::T / 2][Cfg::NCH], const float *gs,
                                          const float *vb) {
   constexpr int DPW = Cfg::DPW, PW = Cfg::PW, NC = Cfg::NC, T = Cfg::T;
   constexpr int NK = K1 - K0;
-  float Gr[NK][T];
+  float2 Gr[NK][T / 2];  // coefficient pairs (pixel 2tp, 2tp+1)
 #pragma unroll
   for (int kk = 0; kk < NK; ++kk) {
     const int k = K0 + kk;
     if (Cfg::WHICH == 1) {
       const float4 g0 = lds128(gs + k * Cfg::GC);
       const float4 g1 = lds128(gs + k * Cfg::GC + 4);
-      Gr[kk][0] = g0.x; Gr[kk][1] = g0.y; Gr[kk][2] = g0.z; Gr[kk][3] = g0.w;
-      Gr[kk][4] = g1.x; Gr[kk][5] = g1.y; Gr[kk][6] = g1.z; Gr[kk][7] = g1.w;
+      Gr[kk][0] = make_float2(g0.x, g0.y); Gr[kk][1] = make_float2(g0.z, g0.w);
+      Gr[kk][2] = make_float2(g1.x, g1.y); Gr[kk][3] = make_float2(g1.z, g1.w);
     } else {
       const float *gp = gs + (PW - 1 - k) * NC + k * DPW;
       if ((k * DPW) % 4 == 0) {
         const float4 g0 = lds128(gp), g1 = lds128(gp + 4);
-        Gr[kk][0] = g0.x; Gr[kk][1] = g0.y; Gr[kk][2] = g0.z; Gr[kk][3] = g0.w;
-        Gr[kk][4] = g1.x; Gr[kk][5] = g1.y; Gr[kk][6] = g1.z; Gr[kk][7] = g1.w;
+        Gr[kk][0] = make_float2(g0.x, g0.y); Gr[kk][1] = make_float2(g0.z, g0.w);
+        Gr[kk][2] = make_float2(g1.x, g1.y); Gr[kk][3] = make_float2(g1.z, g1.w);
       } else if ((k * DPW) % 2 == 0) {
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float2 g = *reinterpret_cast<const float2 *>(gp + 2 * h);
-          Gr[kk][2 * h] = g.x;
-          Gr[kk][2 * h + 1] = g.y;
-        }
+        for (int h = 0; h < 4; ++h) Gr[kk][h] = *reinterpret_cast<const float2 *>(gp + 2 * h);
       } else {
 #pragma unroll
-        for (int t = 0; t < T; ++t) Gr[kk][t] = gp[t];
+        for (int h = 0; h < 4; ++h) Gr[kk][h] = make_float2(gp[2 * h], gp[2 * h + 1]);
       }
     }
   }
@@ -126,14 +122,32 @@ __device__ __forceinline__ void bwd_pass(float (&acc)[Cfg::T][Cfg::NCH], const f
 #pragma unroll
     for (int sg = 0; sg < NL; ++sg) {
       const float4 v4 = lds128(vb + ci * 8 * NC + MB + 4 * sg);
-      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      if constexpr (DPW % 2 == 0) {
+        // pixel pair tp meets window pair tp + k'*DPW/2: one FFMA2 per (tp, k')
+        const float2 vp[2] = {make_float2(v4.x, v4.y), make_float2(v4.z, v4.w)};
 #pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
+        for (int uu = 0; uu < 2; ++uu) {
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const int d = MB + 4 * sg + uu - t;  // = k' * DPW
-          if (d >= 0 && d % DPW == 0 && d / DPW >= K0 && d / DPW < K1)
-            acc[t][ci] = fmaf(Gr[d / DPW - K0][t], v[uu], acc[t][ci]);
+          for (int tp = 0; tp < T / 2; ++tp) {
+            const int d = MB / 2 + 2 * sg + uu - tp;  // = k' * DPW / 2
+            if (d >= 0 && d % (DPW / 2) == 0 && d / (DPW / 2) >= K0 && d / (DPW / 2) < K1)
+              acc2[tp][ci] = __ffma2_rn(Gr[d / (DPW / 2) - K0][tp], vp[uu], acc2[tp][ci]);
+          }
+        }
+      } else {
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int d = MB + 4 * sg + uu - t;  // = k' * DPW
+            if (d >= 0 && d % DPW == 0 && d / DPW >= K0 && d / DPW < K1) {
+              const float2 g = Gr[d / DPW - K0][t / 2];
+              float2 &r = acc2[t / 2][ci];
+              if (t % 2 == 0) r.x = fmaf(g.x, v[uu], r.x);
+              else r.y = fmaf(g.y, v[uu], r.y);
+            }
+          }
         }
       }
     }
@@ -148,9 +162,11 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
   extern __shared__ __align__(128) float smem[];
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + NST * Cfg::STAGE_FLOATS);
   uint64_t *empty_bar = full_bar + NST;
+  BUnit &px = *reinterpret_cast<BUnit *>(empty_bar + NST);  // producer-side unit (thread 0 only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int li = lane >> 3, lj = lane & 7;
+  // li fastest: the 4 row-lanes that read the same `other` address are adjacent (2-cycle LDS.128)
+  const int li = lane & 3, lj = lane >> 2;
   const int cgw = warp & 3, cset = warp >> 2;
 
   if (tid == 0) {
@@ -169,7 +185,6 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
   // ---- producer (thread 0): walks (unit, source row) NST-1 steps ahead of the math
   int pu = blockIdx.x, ps = 0;
   uint32_t pq = 0;
-  BUnit px;
   if (tid == 0 && pu < nunits) decode_bunit<Cfg>(p, pu, px);
   auto issue = [&]() {
     if (pu >= nunits) return;
@@ -220,11 +235,11 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
     const int offg = Cfg::OTHER_FLOATS +
                      (Cfg::WHICH == 1 ? li * Cfg::GLI + cgw * T + 4 * li : li * PW * NC + cgw * T);
 
-    float acc[T][Cfg::NCH];
+    float2 acc[T / 2][Cfg::NCH];  // pixel pairs x channels
 #pragma unroll
-    for (int t = 0; t < T; ++t)
+    for (int t = 0; t < T / 2; ++t)
 #pragma unroll
-      for (int c = 0; c < Cfg::NCH; ++c) acc[t][c] = 0.f;
+      for (int c = 0; c < Cfg::NCH; ++c) acc[t][c] = make_float2(0.f, 0.f);
 
     for (int step = 0; step < x.nsteps; ++step, ++q) {
       const int st = q % NST;
@@ -255,10 +270,10 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
       for (int ci = 0; ci < Cfg::NCH; ++ci) {
         if (x0 < p.W)
           *reinterpret_cast<float4 *>(o + (size_t)ci * 8 * HW) =
-              make_float4(acc[0][ci], acc[1][ci], acc[2][ci], acc[3][ci]);
+              make_float4(acc[0][ci].x, acc[0][ci].y, acc[1][ci].x, acc[1][ci].y);
         if (x0 + 4 < p.W)
           *reinterpret_cast<float4 *>(o + (size_t)ci * 8 * HW + 4) =
-              make_float4(acc[4][ci], acc[5][ci], acc[6][ci], acc[7][ci]);
+              make_float4(acc[2][ci].x, acc[2][ci].y, acc[3][ci].x, acc[3][ci].y);
       }
     }
   }

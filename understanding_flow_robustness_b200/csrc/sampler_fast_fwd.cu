@@ -56,7 +56,7 @@ struct FwdCfg {
   static constexpr int STAGE_FLOATS = IN2_FLOATS + IN1_FLOATS;
   static constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
   static_assert((IN2_FLOATS * 4) % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA destination alignment");
-  static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 128;
+  static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 256;
   static constexpr int SLOTS = 64;                     // items per unit (8 warps x 8)
 };
 
@@ -114,10 +114,15 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
   extern __shared__ __align__(128) float smem[];  // NST stages, then the mbarriers
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + NST * Cfg::STAGE_FLOATS);
   uint64_t *empty_bar = full_bar + NST;
+  Unit &px = *reinterpret_cast<Unit *>(empty_bar + NST);  // producer-side unit (thread 0 only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int li = lane >> 3;  // pixel row inside the group (0..3)
-  const int lj = lane & 7;   // item column inside the warp (0..7)
+  // Lane layout (measured on B200, scripts/probe_sm.py: an LDS.128 costs max(2, runs/8) cycles where
+  // a "run" is a maximal group of ADJACENT lanes reading the same 16 bytes -- sharing between
+  // non-adjacent lanes is not merged).  The 4 lanes of a quad are the 4 pixel rows; quad q takes
+  // item (q - li) mod 8, so lanes of a quad that read the same in2 row (li + e constant) are adjacent.
+  const int li = lane & 3;                  // pixel row inside the group (0..3)
+  const int lj = ((lane >> 2) - li) & 7;    // item column inside the warp (0..7)
 
   if (tid == 0) {
     tma_prefetch_desc(&map1);
@@ -136,7 +141,6 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
   // ---- producer state (thread 0 only): the load stream runs NST-1 chunks ahead of the math
   int pu = blockIdx.x, pc = 0;
   uint32_t pq = 0;
-  Unit px;
   if (tid == 0 && pu < nunits) decode_unit<Cfg>(p, pu, px);
   auto issue = [&]() {
     if (pu >= nunits) return;
@@ -173,11 +177,12 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
     const int off2 = rbox * NC2 + cb;
     const int off1 = Cfg::IN2_FLOATS + li * NC1 + cb;
 
-    float acc[Cfg::T][PW];
+    // accumulators as pixel pairs: acc2[tp][k] = (acc[2tp][k], acc[2tp+1][k]) -> packed FFMA2
+    float2 acc2[Cfg::T / 2][PW];
 #pragma unroll
-    for (int t = 0; t < Cfg::T; ++t)
+    for (int t = 0; t < Cfg::T / 2; ++t)
 #pragma unroll
-      for (int k = 0; k < PW; ++k) acc[t][k] = 0.f;
+      for (int k = 0; k < PW; ++k) acc2[t][k] = make_float2(0.f, 0.f);
 
     for (int c = 0; c < cpu; ++c, ++q) {
       const int st = q % NST;
@@ -192,18 +197,41 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
       for (int cc = 0; cc < CC; ++cc) {
         const float4 a0 = lds128(sa + cc * b200::kRowsPerGroup * NC1);
         const float4 a1 = lds128(sa + cc * b200::kRowsPerGroup * NC1 + 4);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        if constexpr (DPW % 2 == 0) {
+          // pixel pair tp = (2tp, 2tp+1) meets window pair tp + k*DPW/2: one FFMA2 per (tp, k)
+          const float2 ap[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w),
+                                make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
 #pragma unroll
-        for (int sgm = 0; sgm < Cfg::WIN / 4; ++sgm) {
-          const float4 v4 = lds128(sb + cc * NRB * NC2 + 4 * sgm);
-          const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+          for (int sgm = 0; sgm < Cfg::WIN / 4; ++sgm) {
+            const float4 v4 = lds128(sb + cc * NRB * NC2 + 4 * sgm);
+            const float2 vp[2] = {make_float2(v4.x, v4.y), make_float2(v4.z, v4.w)};
 #pragma unroll
-          for (int uu = 0; uu < 4; ++uu) {
+            for (int uu = 0; uu < 2; ++uu) {
 #pragma unroll
-            for (int t = 0; t < Cfg::T; ++t) {
-              const int d = 4 * sgm + uu - t;  // = k * DPW
-              if (d >= 0 && d % DPW == 0 && d / DPW < PW)
-                acc[t][d / DPW] = fmaf(a[t], v[uu], acc[t][d / DPW]);
+              for (int tp = 0; tp < 4; ++tp) {
+                const int d = 2 * sgm + uu - tp;  // = k * DPW / 2
+                if (d >= 0 && d % (DPW / 2) == 0 && d / (DPW / 2) < PW)
+                  acc2[tp][d / (DPW / 2)] = __ffma2_rn(ap[tp], vp[uu], acc2[tp][d / (DPW / 2)]);
+              }
+            }
+          }
+        } else {
+          const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int sgm = 0; sgm < Cfg::WIN / 4; ++sgm) {
+            const float4 v4 = lds128(sb + cc * NRB * NC2 + 4 * sgm);
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+#pragma unroll
+              for (int t = 0; t < Cfg::T; ++t) {
+                const int d = 4 * sgm + uu - t;  // = k * DPW
+                if (d >= 0 && d % DPW == 0 && d / DPW < PW) {
+                  float2 &r = acc2[t / 2][d / DPW];
+                  if (t % 2 == 0) r.x = fmaf(a[t], v[uu], r.x);
+                  else r.y = fmaf(a[t], v[uu], r.y);
+                }
+              }
             }
           }
         }
@@ -221,8 +249,8 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
       float *o = out + (((size_t)x.n * PH + (e + Cfg::RH)) * PW) * HW + (size_t)h * p.W + w0;
 #pragma unroll
       for (int k = 0; k < PW; ++k) {
-        if (lo_ok) stg128(o + k * HW, acc[0][k], acc[1][k], acc[2][k], acc[3][k]);
-        if (hi_ok) stg128(o + k * HW + 4, acc[4][k], acc[5][k], acc[6][k], acc[7][k]);
+        if (lo_ok) stg128(o + k * HW, acc2[0][k].x, acc2[0][k].y, acc2[1][k].x, acc2[1][k].y);
+        if (hi_ok) stg128(o + k * HW + 4, acc2[2][k].x, acc2[2][k].y, acc2[3][k].x, acc2[3][k].y);
       }
       // row displacements clipped away for the whole group: zero planes
       const int nclip = PH - x.ne;
