@@ -13,12 +13,14 @@ L = _lib.lib()
 res = {}
 st = _lib.current_stream(torch.device("cuda:0"))
 v = ctypes.c_float()
-for warps in (8, 16):
+for warps in (16,):
     for pat in range(11):
         _lib.check(L.b200corr_probe_lds(pat, warps, 2000, ctypes.byref(v), st), "probe_lds")
         res[f"lds_p{pat}_w{warps}"] = round(v.value, 3)
 _lib.check(L.b200corr_measure_fp32_peak(20000, ctypes.byref(v), st), "fp32 peak")
 res["fp32_peak_tflops"] = round(v.value, 2)
+_lib.check(L.b200corr_probe_ffma2_peak(4000, ctypes.byref(v), st), "ffma2 peak")
+res["ffma2_peak_tflops"] = round(v.value, 2)
 _lib.check(L.b200corr_probe_ffma_toeplitz(2000, ctypes.byref(v), st), "toeplitz")
 res["ffma_toeplitz_tflops"] = round(v.value, 2)
 print(json.dumps(res, indent=1))

@@ -1,0 +1,300 @@
+"""Parity of the RAFT correlation kernels (all-pairs volume + pyramid, lookup, alt_cuda_corr) through
+the C-ABI against the numpy oracle, the reference-generated golden vectors and -- for the pieces
+whose reference arithmetic lives in torch (matmul / avg_pool2d / grid_sample) -- torch itself on the
+same device.  Tolerances:
+  fp32 volume / pyramid  : <= 1e-5 * max|vol|
+  tf32 volume            : |d| <= 2^-10 * scale * sum_c|f1 f2|  (+ fp32 accumulation slack)
+  lookup vs grid_sample  : <= 1e-4 * max|vol| (coordinate round trip); vs the oracle's restatement
+                           of the CUDA arithmetic: <= 2e-6 * max|vol|
+  alt vs CorrBlock       : <= 1e-4 * max|out|
+"""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+RAFT = sorted(glob.glob(os.path.join(GOLDEN, "raft_*.npz")))
+
+
+def _cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _maxabs(x):
+    return float(np.abs(x).max())
+
+
+def _torch_corrblock(f1, f2, coords, L, r):
+    """models/raft/corr.py restated with torch ops (the reference's third-party arithmetic)."""
+    B, C, H, W = f1.shape
+    corr = torch.matmul(f1.view(B, C, H * W).transpose(1, 2), f2.view(B, C, H * W))
+    corr = corr.view(B, H, W, 1, H, W) / torch.sqrt(torch.tensor(C).float())
+    corr = corr.reshape(B * H * W, 1, H, W)
+    pyr = [corr]
+    for _ in range(L - 1):
+        corr = F.avg_pool2d(corr, 2, stride=2)
+        pyr.append(corr)
+    c = coords.permute(0, 2, 3, 1)
+    outs = []
+    for i in range(L):
+        dx = torch.linspace(-r, r, 2 * r + 1, device=f1.device)
+        dy = torch.linspace(-r, r, 2 * r + 1, device=f1.device)
+        delta = torch.stack(torch.meshgrid(dy, dx, indexing="ij"), axis=-1)
+        cl = c.reshape(B * H * W, 1, 1, 2) / 2 ** i + delta.view(1, 2 * r + 1, 2 * r + 1, 2)
+        Hl, Wl = pyr[i].shape[-2:]
+        xg, yg = cl.split([1, 1], dim=-1)
+        grid = torch.cat([2 * xg / (Wl - 1) - 1, 2 * yg / (Hl - 1) - 1], dim=-1)
+        outs.append(F.grid_sample(pyr[i], grid, align_corners=True).view(B, H, W, -1))
+    return torch.cat(outs, dim=-1).permute(0, 3, 1, 2).contiguous().float(), pyr
+
+
+@pytest.mark.parametrize("path", RAFT, ids=[os.path.basename(p)[:-4] for p in RAFT])
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_pyramid_vs_reference_golden(path, precision):
+    from understanding_flow_robustness_b200 import raft_corr
+    z = np.load(path)
+    L = int(z["levels"])
+    f1, f2 = _cuda(z["f1"]), _cuda(z["f2"])
+    pyr = raft_corr.allpairs_pyramid(f1, f2, L, precision)
+    C = z["f1"].shape[1]
+    # sum_c |f1 f2| / sqrt(C): the scale of the TF32 rounding bound
+    absdot = np.einsum("bcm,bcn->bmn", np.abs(z["f1"]).reshape(*z["f1"].shape[:2], -1),
+                       np.abs(z["f2"]).reshape(*z["f2"].shape[:2], -1)).max() / math.sqrt(C)
+    for l in range(L):
+        ref = z[f"pyr{l}"]
+        got = pyr[l].cpu().numpy()
+        assert got.shape == ref.shape
+        tol = 1e-5 * _maxabs(z["pyr0"]) if precision == "fp32" else 2.0 ** -10 * absdot + 1e-5 * _maxabs(z["pyr0"])
+        assert _maxabs(got - ref) <= tol, (l, _maxabs(got - ref), tol)
+
+
+@pytest.mark.parametrize("path", RAFT, ids=[os.path.basename(p)[:-4] for p in RAFT])
+def test_lookup_vs_reference_golden(path):
+    """Lookup from the REFERENCE pyramid isolates the sampling arithmetic."""
+    from oracle import raft_oracle
+    from understanding_flow_robustness_b200 import raft_corr
+    z = np.load(path)
+    L, r = int(z["levels"]), int(z["radius"])
+    B, _, H, W = z["coords"].shape
+    pyr = [_cuda(z[f"pyr{l}"]) for l in range(L)]
+    coords = _cuda(z["coords"])
+    scale = _maxabs(z["out"])
+    out = raft_corr.lookup_forward(pyr, coords, r, H, W, "grid_sample").cpu().numpy()
+    assert out.shape == z["out"].shape
+    assert _maxabs(out - z["out"]) <= 1e-4 * scale                      # golden made by torch on CPU
+    ora = raft_oracle.lookup([z[f"pyr{l}"] for l in range(L)], z["coords"], r, unnorm="cuda")
+    assert _maxabs(out - ora) <= 2e-6 * scale                           # same arithmetic restated
+    # grid_sample on this device: the reference's actual code path on a GPU
+    tref, _ = None, None
+    pt = [p for p in pyr]
+    c = coords.permute(0, 2, 3, 1)
+    outs = []
+    for i in range(L):
+        d = torch.linspace(-r, r, 2 * r + 1, device="cuda")
+        delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), axis=-1)
+        cl = c.reshape(B * H * W, 1, 1, 2) / 2 ** i + delta.view(1, 2 * r + 1, 2 * r + 1, 2)
+        Hl, Wl = pt[i].shape[-2:]
+        xg, yg = cl.split([1, 1], dim=-1)
+        grid = torch.cat([2 * xg / (Wl - 1) - 1, 2 * yg / (Hl - 1) - 1], dim=-1)
+        outs.append(F.grid_sample(pt[i], grid, align_corners=True).view(B, H, W, -1))
+    tref = torch.cat(outs, dim=-1).permute(0, 3, 1, 2).contiguous().cpu().numpy()
+    assert _maxabs(out - tref) <= 2e-6 * scale
+    # direct mode: within the documented round-trip bound of the reference
+    outd = raft_corr.lookup_forward(pyr, coords, r, H, W, "direct").cpu().numpy()
+    assert _maxabs(outd - z["out"]) <= 1e-4 * scale
+
+
+TC_SHAPES = [(1, 32, 8, 32), (2, 64, 11, 20), (1, 40, 16, 36), (1, 256, 24, 64), (3, 8, 5, 8)]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES, ids=[str(s) for s in TC_SHAPES])
+def test_tcgen05_volume_ragged_shapes(shape):
+    """tcgen05 path (W % 4 == 0) with M / patch tails, channel padding, and 1..5 levels."""
+    from understanding_flow_robustness_b200 import raft_corr
+    B, C, H, W = shape
+    torch.manual_seed(B * 1000 + C + H + W)
+    f1 = torch.randn(B, C, H, W, device="cuda")
+    f2 = torch.randn(B, C, H, W, device="cuda")
+    L = 1
+    while min(H, W) // 2 ** L >= 1 and L < 5:
+        L += 1
+    pyr = raft_corr.allpairs_pyramid(f1, f2, L, "tf32")
+    a = f1.double().view(B, C, -1)
+    b = f2.double().view(B, C, -1)
+    exact = torch.einsum("bcm,bcn->bmn", a, b) / math.sqrt(C)
+    bound = 2.0 ** -10 * torch.einsum("bcm,bcn->bmn", a.abs(), b.abs()) / math.sqrt(C) + 1e-5
+    v0 = pyr[0].view(B, H * W, H * W).double()
+    assert bool(((v0 - exact).abs() <= bound).all()), float(((v0 - exact).abs() - bound).max())
+    ref = v0.float().view(B * H * W, 1, H, W)
+    for l in range(1, L):
+        ref = F.avg_pool2d(ref, 2, stride=2)
+        assert pyr[l].shape == ref.shape
+        assert float((pyr[l] - ref).abs().max()) <= 2e-6 * float(v0.abs().max()) + 1e-7, l
+    # exact kernel agrees with the fp64 contraction to fp32 accuracy
+    e32 = raft_corr.allpairs_pyramid(f1, f2, 1, "fp32")[0].view(B, H * W, H * W).double()
+    assert float((e32 - exact).abs().max()) <= 1e-5 * float(exact.abs().max())
+
+
+def test_corrblock_end_to_end_and_autograd():
+    """CorrBlock (fp32 volume) forward + gradients w.r.t. both feature maps vs torch autograd through
+    matmul / avg_pool2d / grid_sample; two lookups accumulate into one gradient pyramid."""
+    from understanding_flow_robustness_b200 import CorrBlock, coords_grid
+    torch.manual_seed(3)
+    B, C, H, W, L, r = 2, 16, 12, 16, 3, 3
+    f1 = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+    f2 = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+    ca = coords_grid(B, H, W, "cuda") + 2.5 * torch.randn(B, 2, H, W, device="cuda")
+    cb = coords_grid(B, H, W, "cuda") + 9.0 * torch.randn(B, 2, H, W, device="cuda")
+    blk = CorrBlock(f1, f2, num_levels=L, radius=r, precision="fp32")
+    oa, ob = blk(ca), blk(cb)
+    ga, gb = torch.randn_like(oa), torch.randn_like(ob)
+    (oa * ga).sum().add((ob * gb).sum()).backward()
+    g1, g2 = f1.grad.clone(), f2.grad.clone()
+    f1.grad = f2.grad = None
+    ra, _ = _torch_corrblock(f1, f2, ca, L, r)
+    rb, _ = _torch_corrblock(f1, f2, cb, L, r)
+    (ra * ga).sum().add((rb * gb).sum()).backward()
+    s = float(ra.abs().max())
+    assert float((oa - ra).abs().max()) <= 1e-5 * s and float((ob - rb).abs().max()) <= 1e-5 * s
+    assert float((g1 - f1.grad).abs().max()) <= 2e-5 * float(f1.grad.abs().max())
+    assert float((g2 - f2.grad).abs().max()) <= 2e-5 * float(f2.grad.abs().max())
+    # no-grad construction gives the same values and the public pyramid layout (corr.py:66-67)
+    with torch.no_grad():
+        blk2 = CorrBlock(f1, f2, num_levels=L, radius=r, precision="fp32")
+        assert [tuple(v.shape) for v in blk2.get_corr_pyramid()] == [(B * H * W, 1, H // 2 ** l, W // 2 ** l) for l in range(L)]
+        assert float((blk2(ca) - oa).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("path", RAFT[:2], ids=[os.path.basename(p)[:-4] for p in RAFT[:2]])
+def test_alt_corr_vs_oracle_and_corrblock(path):
+    from oracle import raft_oracle
+    from understanding_flow_robustness_b200 import AlternateCorrBlock, alt_cuda_corr
+    z = np.load(path)
+    L, r = int(z["levels"]), int(z["radius"])
+    f1n = np.ascontiguousarray(z["f1"].transpose(0, 2, 3, 1))
+    f2n = np.ascontiguousarray(z["f2"].transpose(0, 2, 3, 1))
+    B, H, W, C = f1n.shape
+    coords = np.ascontiguousarray(z["coords"].transpose(0, 2, 3, 1).reshape(B, 1, H, W, 2))
+    (corr,) = alt_cuda_corr.forward(_cuda(f1n), _cuda(f2n), _cuda(coords), r)
+    ref = raft_oracle.alt_corr_forward(f1n, f2n, coords, r)
+    assert corr.shape == ref.shape
+    assert _maxabs(corr.cpu().numpy() - ref) <= 1e-5 * _maxabs(ref)
+    g = np.random.default_rng(1).standard_normal(ref.shape).astype(np.float32)
+    g1, g2, gc = alt_cuda_corr.backward(_cuda(f1n), _cuda(f2n), _cuda(coords), _cuda(g), r)
+    r1, r2, rc = raft_oracle.alt_corr_backward(f1n, f2n, coords, g, r)
+    assert _maxabs(g1.cpu().numpy() - r1) <= 1e-5 * _maxabs(r1)
+    assert _maxabs(g2.cpu().numpy() - r2) <= 1e-5 * _maxabs(r2)
+    assert not gc.any()
+    # AlternateCorrBlock == CorrBlock output (golden) by linearity of the average pool
+    alt = AlternateCorrBlock(_cuda(z["f1"]), _cuda(z["f2"]), num_levels=L, radius=r)(_cuda(z["coords"]))
+    assert alt.shape == z["out"].shape
+    assert _maxabs(alt.cpu().numpy() - z["out"]) <= 1e-4 * _maxabs(z["out"])
+
+
+def test_alt_corr_multi_n_and_autograd():
+    from oracle import raft_oracle
+    from understanding_flow_robustness_b200 import AlternateCorrBlock, alt_cuda_corr, coords_grid
+    rng = np.random.default_rng(11)
+    B, N, H, W, C, r = 2, 3, 6, 9, 36, 2
+    f1 = rng.standard_normal((B, H, W, C)).astype(np.float32)
+    f2 = rng.standard_normal((B, 4, 5, C)).astype(np.float32)       # fmap2 at another resolution
+    coords = (rng.uniform(-3, 8, (B, N, H, W, 2))).astype(np.float32)
+    (corr,) = alt_cuda_corr.forward(_cuda(f1), _cuda(f2), _cuda(coords), r)
+    ref = raft_oracle.alt_corr_forward(f1, f2, coords, r)
+    assert _maxabs(corr.cpu().numpy() - ref) <= 1e-5 * _maxabs(ref)
+    g = rng.standard_normal(ref.shape).astype(np.float32)
+    g1, g2, _ = alt_cuda_corr.backward(_cuda(f1), _cuda(f2), _cuda(coords), _cuda(g), r)
+    r1, r2, _ = raft_oracle.alt_corr_backward(f1, f2, coords, g, r)
+    assert _maxabs(g1.cpu().numpy() - r1) <= 1e-5 * _maxabs(r1)
+    assert _maxabs(g2.cpu().numpy() - r2) <= 1e-5 * _maxabs(r2)
+    # the block is differentiable (the reference's is not): gradient == CorrBlock's (fp32, direct)
+    from understanding_flow_robustness_b200 import CorrBlock
+    torch.manual_seed(0)
+    a = torch.randn(1, 8, 8, 12, device="cuda", requires_grad=True)
+    b = torch.randn(1, 8, 8, 12, device="cuda", requires_grad=True)
+    c = coords_grid(1, 8, 12, "cuda") + 1.7 * torch.randn(1, 2, 8, 12, device="cuda")
+    oa = AlternateCorrBlock(a, b, num_levels=2, radius=2)(c)
+    w = torch.randn_like(oa)
+    (oa * w).sum().backward()
+    ga, gb = a.grad.clone(), b.grad.clone()
+    a.grad = b.grad = None
+    oc = CorrBlock(a, b, num_levels=2, radius=2, precision="fp32", lookup_mode="direct")(c)
+    (oc * w).sum().backward()
+    assert float((oa - oc).abs().max()) <= 1e-5 * float(oc.abs().max())
+    assert float((ga - a.grad).abs().max()) <= 1e-4 * float(a.grad.abs().max())
+    assert float((gb - b.grad).abs().max()) <= 1e-4 * float(b.grad.abs().max())
+
+
+def test_alt_corr_vs_compiled_reference_extension():
+    """Live pin against the reference's own alt_cuda_corr compiled for sm_100a (oracle/_ref)."""
+    from oracle import build_ref_cuda
+    if not os.path.exists(build_ref_cuda.so_path("ref_alt_cuda_corr")):
+        pytest.skip("oracle/_ref/ref_alt_cuda_corr not built")
+    try:
+        ref_mod = build_ref_cuda.load_module("ref_alt_cuda_corr")
+    except Exception as e:  # ABI mismatch on the box: the numpy oracle still pins the kernel
+        pytest.skip(f"reference extension not loadable: {e}")
+    from understanding_flow_robustness_b200 import alt_cuda_corr
+    torch.manual_seed(5)
+    B, H, W, C, r = 2, 16, 24, 64, 4
+    f1 = torch.randn(B, H, W, C, device="cuda")
+    f2 = torch.randn(B, H, W, C, device="cuda")
+    coords = (torch.rand(B, 1, H, W, 2, device="cuda") * torch.tensor([W + 6.0, H + 6.0], device="cuda") - 3.0)
+    (ours,) = alt_cuda_corr.forward(f1, f2, coords, r)
+    (theirs,) = ref_mod.forward(f1, f2, coords, r)
+    torch.cuda.synchronize()
+    assert float((ours - theirs).abs().max()) <= 1e-5 * float(theirs.abs().max())
+    g = torch.randn_like(ours)
+    o1, o2, _ = alt_cuda_corr.backward(f1, f2, coords, g, r)
+    t1, t2, _ = ref_mod.backward(f1, f2, coords, g, r)
+    torch.cuda.synchronize()
+    assert float((o1 - t1).abs().max()) <= 2e-5 * float(t1.abs().max())
+    assert float((o2 - t2).abs().max()) <= 2e-5 * float(t2.abs().max())
+
+
+def test_full_size_raft_properties():
+    """BASELINE config 3: B=4, 256x48x160, 4 levels, radius 4 -- size-independent properties."""
+    from understanding_flow_robustness_b200 import AlternateCorrBlock, CorrBlock, coords_grid
+    torch.manual_seed(0)
+    B, C, H, W = 4, 256, 48, 160
+    f1 = torch.randn(B, C, H, W, device="cuda")
+    f2 = torch.randn(B, C, H, W, device="cuda")
+    blk = CorrBlock(f1, f2, num_levels=4, radius=4)
+    pyr = blk.get_corr_pyramid()
+    assert [tuple(v.shape) for v in pyr] == [(B * H * W, 1, 48, 160), (B * H * W, 1, 24, 80),
+                                             (B * H * W, 1, 12, 40), (B * H * W, 1, 6, 20)]
+    # random entries of level 0 against fp64 dot products, within the TF32 bound
+    g = torch.Generator(device="cuda").manual_seed(1)
+    bi = torch.randint(0, B, (4096,), device="cuda", generator=g)
+    m = torch.randint(0, H * W, (4096,), device="cuda", generator=g)
+    n = torch.randint(0, H * W, (4096,), device="cuda", generator=g)
+    a = f1.view(B, C, -1)[bi, :, m].double()
+    b = f2.view(B, C, -1)[bi, :, n].double()
+    exact = (a * b).sum(1) / 16.0
+    bound = 2.0 ** -10 * (a.abs() * b.abs()).sum(1) / 16.0 + 1e-5
+    got = pyr[0].view(B, H * W, H * W)[bi, m, n].double()
+    assert bool(((got - exact).abs() <= bound).all())
+    # every pooled level is the 2x2 mean of the level below
+    for l in range(1, 4):
+        ref = F.avg_pool2d(pyr[l - 1][: 2 * H * W], 2, stride=2)
+        assert float((pyr[l][: 2 * H * W] - ref).abs().max()) <= 1e-5
+    # lookup at integer coordinates (direct mode) returns volume entries exactly
+    c = coords_grid(B, H, W, "cuda")
+    out = CorrBlock(f1, f2, 4, 4, lookup_mode="direct")(c)
+    assert out.shape == (B, 324, H, W)
+    centre = out[:, 4 * 9 + 4]                      # level 0, zero offset
+    diag = pyr[0].view(B, H * W, H * W).diagonal(dim1=1, dim2=2).reshape(B, H, W)
+    assert float((centre - diag).abs().max()) == 0.0
+    # alternate path == volume path (same TF32 question aside: compare against the fp32 volume)
+    c2 = c + 3.0 * torch.randn(B, 2, H, W, device="cuda", generator=g)
+    ref = CorrBlock(f1[:1], f2[:1], 4, 4, precision="fp32", lookup_mode="direct")(c2[:1])
+    alt = AlternateCorrBlock(f1[:1], f2[:1], 4, 4)(c2[:1])
+    assert float((alt - ref).abs().max()) <= 1e-4 * float(ref.abs().max())

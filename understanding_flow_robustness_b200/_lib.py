@@ -19,10 +19,21 @@ PROTOTYPES = {
     "b200corr_sampler_forward": (c_int, [c_void_p] * 4 + [c_size_t] + [c_int] * 17 + [c_void_p]),
     "b200corr_sampler_backward": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 17 + [c_void_p]),
     "b200corr_sampler_uses_fast_path": (c_int, [c_int] * 18),
+    "b200corr_allpairs_workspace_bytes": (c_size_t, [c_int] * 5),
+    "b200corr_allpairs_pyramid": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int,
+                                          c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "b200corr_lookup_forward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_int,
+                                        c_int, c_int, c_int, c_void_p]),
+    "b200corr_lookup_backward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_int,
+                                         c_int, c_int, c_int, c_void_p]),
+    "b200corr_pyramid_backward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),
+    "b200corr_altcorr_forward": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
+    "b200corr_altcorr_backward": (c_int, [c_void_p] * 7 + [c_int] * 8 + [c_void_p]),
     "b200corr_measure_fp32_peak": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p]),
     "b200corr_launch_count": (ctypes.c_uint64, []),
     "b200corr_probe_lds": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float), c_void_p]),
     "b200corr_probe_ffma_toeplitz": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p]),
+    "b200corr_probe_ffma2_peak": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p]),
 }
 
 
@@ -57,3 +68,11 @@ def current_stream(device):
 
 def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (the `h_levels` arguments of the C ABI)."""
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr

@@ -1,0 +1,256 @@
+// altcorr.cu -- on-the-fly windowed correlation: drop-in for alt_cuda_corr.forward / .backward.
+//
+// Reference: models/alt_cuda_corr/correlation_kernel.cu:18-119 (forward), :122-256 (backward),
+// checks and bindings models/alt_cuda_corr/correlation.cpp:23-54.  Semantics:
+//   s[iy][ix] = <fmap1[b,h,w,:], fmap2[b, floor(y)-r+iy, floor(x)-r+ix, :]>   (0 outside fmap2)
+//   corr[b,n, ix*(2r+1)+iy, h,w] = (1-dy)(1-dx) s[iy][ix] + (1-dy)dx s[iy][ix+1]
+//                                 + dy(1-dx) s[iy+1][ix] + dy dx s[iy+1][ix+1]
+// with (x, y) = coords[b,n,h,w,:], dx = x - floor(x), dy = y - floor(y); no 1/sqrt(C) factor.
+//
+// The reference stages 32-channel tiles of both maps per 4x8 query block and loops the (2r+2)^2
+// window serially with one barrier per window point.  Here one warp owns one query: the query's
+// feature vector lives in registers (lane = channel slice), every window pixel of fmap2 is one
+// fully coalesced C*4-byte read (NHWC), the (2r+2)^2 partial dot products stay in registers and
+// are reduced across lanes once at the end through a padded shared-memory transpose; the 8 queries
+// of a CTA then write their (2r+1)^2 outputs as 32-byte sectors.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxVec = 4;   // float4 per lane: C <= 512
+
+template <int R>
+struct AGeo {
+  static constexpr int RD = 2 * R + 1;
+  static constexpr int WN = 2 * R + 2;
+  static constexpr int NW = WN * WN;
+  static constexpr int NCHUNK = (NW + 31) / 32;
+};
+
+template <int R, int NV>
+__global__ void __launch_bounds__(256)
+altcorr_fwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2,
+                   const float *__restrict__ coords, float *__restrict__ corr, int B, int N, int H1,
+                   int W1, int H2, int W2, int C) {
+  using G = AGeo<R>;
+  __shared__ float red[8][32][33];
+  __shared__ float S[8][G::NCHUNK * 32];
+  __shared__ float O[G::RD * G::RD][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW1 = H1 * W1;
+  const int q0 = blockIdx.x * 8, n = blockIdx.y, b = blockIdx.z;
+  const int q = q0 + warp;
+  const bool q_ok = q < HW1;
+  const int nvec = C >> 2;
+
+  float x = 0.f, y = 0.f;
+  float4 a[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q_ok) {
+    const float *cp = coords + (((size_t)b * N + n) * HW1 + q) * 2;
+    x = cp[0];
+    y = cp[1];
+    const float4 *p1 = reinterpret_cast<const float4 *>(f1 + ((size_t)b * HW1 + q) * C);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < nvec) a[i] = p1[lane + 32 * i];
+  }
+  float fxf = floorf(x), fyf = floorf(y);
+  const float dx = x - fxf, dy = y - fyf;
+  if (!(fabsf(fxf) < 1e8f)) fxf = -1e8f;
+  if (!(fabsf(fyf) < 1e8f)) fyf = -1e8f;
+  const int fx = (int)fxf, fy = (int)fyf;
+
+  float acc[G::NW];
+#pragma unroll
+  for (int iy = 0; iy < G::WN; ++iy) {
+    const int y2 = fy - R + iy;
+#pragma unroll
+    for (int ix = 0; ix < G::WN; ++ix) {
+      const int x2 = fx - R + ix;
+      float s = 0.f;
+      if (q_ok && y2 >= 0 && y2 < H2 && x2 >= 0 && x2 < W2) {
+        const float4 *p2 = reinterpret_cast<const float4 *>(f2 + (((size_t)b * H2 + y2) * W2 + x2) * C);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (lane + 32 * i < nvec) {
+            const float4 v = __ldg(p2 + lane + 32 * i);
+            s = fmaf(a[i].x, v.x, s);
+            s = fmaf(a[i].y, v.y, s);
+            s = fmaf(a[i].z, v.z, s);
+            s = fmaf(a[i].w, v.w, s);
+          }
+      }
+      acc[iy * G::WN + ix] = s;
+    }
+  }
+  // cross-lane reduction, 32 window points at a time: lane l ends up with the sum of point 32c + l
+#pragma unroll
+  for (int c = 0; c < G::NCHUNK; ++c) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c * 32 + j < G::NW) red[warp][j][lane] = acc[c * 32 + j];
+    __syncwarp();
+    float s = 0.f;
+    if (c * 32 + lane < G::NW) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s += red[warp][lane][j];
+    }
+    S[warp][c * 32 + lane] = s;
+    __syncwarp();
+  }
+  // bilinear combination -> (2r+1)^2 outputs, channel = ix * RD + iy
+  for (int k = lane; k < G::RD * G::RD; k += 32) {
+    const int ix = k / G::RD, iy = k - ix * G::RD;
+    const float *s = S[warp];
+    const float v = (1.f - dy) * (1.f - dx) * s[iy * G::WN + ix] + (1.f - dy) * dx * s[iy * G::WN + ix + 1] +
+                    dy * (1.f - dx) * s[(iy + 1) * G::WN + ix] + dy * dx * s[(iy + 1) * G::WN + ix + 1];
+    O[k][warp] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G::RD * G::RD * 8; i += 256) {
+    const int k = i >> 3, qi = i & 7;
+    if (q0 + qi < HW1) corr[(((size_t)b * N + n) * (G::RD * G::RD) + k) * HW1 + q0 + qi] = O[k][qi];
+  }
+}
+
+template <int R, int NV>
+__global__ void __launch_bounds__(256)
+altcorr_bwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2,
+                   const float *__restrict__ coords, const float *__restrict__ cgrad,
+                   float *__restrict__ f1g, float *__restrict__ f2g, int B, int N, int H1, int W1,
+                   int H2, int W2, int C) {
+  using G = AGeo<R>;
+  __shared__ float GS[8][G::NCHUNK * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW1 = H1 * W1;
+  const int q = blockIdx.x * 8 + warp, b = blockIdx.z;
+  if (q >= HW1) return;
+  const int nvec = C >> 2;
+  float4 a[NV], ga[NV];
+  const float4 *p1 = reinterpret_cast<const float4 *>(f1 + ((size_t)b * HW1 + q) * C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ga[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane + 32 * i < nvec) a[i] = p1[lane + 32 * i];
+  }
+  for (int n = 0; n < N; ++n) {
+    const float *cp = coords + (((size_t)b * N + n) * HW1 + q) * 2;
+    const float x = cp[0], y = cp[1];
+    float fxf = floorf(x), fyf = floorf(y);
+    const float dx = x - fxf, dy = y - fyf;
+    if (!(fabsf(fxf) < 1e8f)) fxf = -1e8f;
+    if (!(fabsf(fyf) < 1e8f)) fyf = -1e8f;
+    const int fx = (int)fxf, fy = (int)fyf;
+    // gradient w.r.t. the window dot products (gather form of correlation_kernel.cu:203-218)
+    const float *gq = cgrad + (((size_t)b * N + n) * (G::RD * G::RD)) * HW1 + q;
+    __syncwarp();
+    for (int idx = lane; idx < G::NW; idx += 32) {
+      const int iy = idx / G::WN, ix = idx - iy * G::WN;
+      float g = 0.f;
+      if (ix < G::RD && iy < G::RD) g += (1.f - dy) * (1.f - dx) * gq[(size_t)(ix * G::RD + iy) * HW1];
+      if (ix >= 1 && iy < G::RD) g += (1.f - dy) * dx * gq[(size_t)((ix - 1) * G::RD + iy) * HW1];
+      if (ix < G::RD && iy >= 1) g += dy * (1.f - dx) * gq[(size_t)(ix * G::RD + iy - 1) * HW1];
+      if (ix >= 1 && iy >= 1) g += dy * dx * gq[(size_t)((ix - 1) * G::RD + iy - 1) * HW1];
+      GS[warp][idx] = g;
+    }
+    __syncwarp();
+    for (int idx = 0; idx < G::NW; ++idx) {
+      const int iy = idx / G::WN, ix = idx - iy * G::WN;
+      const int y2 = fy - R + iy, x2 = fx - R + ix;
+      const float g = GS[warp][idx];
+      if (g == 0.f || y2 < 0 || y2 >= H2 || x2 < 0 || x2 >= W2) continue;
+      const size_t off = (((size_t)b * H2 + y2) * W2 + x2) * C;
+      const float4 *p2 = reinterpret_cast<const float4 *>(f2 + off);
+      float *g2 = f2g + off;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (lane + 32 * i < nvec) {
+          const float4 v = __ldg(p2 + lane + 32 * i);
+          ga[i].x = fmaf(g, v.x, ga[i].x);
+          ga[i].y = fmaf(g, v.y, ga[i].y);
+          ga[i].z = fmaf(g, v.z, ga[i].z);
+          ga[i].w = fmaf(g, v.w, ga[i].w);
+          float *d = g2 + 4 * (lane + 32 * i);
+          atomicAdd(d, g * a[i].x);
+          atomicAdd(d + 1, g * a[i].y);
+          atomicAdd(d + 2, g * a[i].z);
+          atomicAdd(d + 3, g * a[i].w);
+        }
+    }
+  }
+  float4 *o = reinterpret_cast<float4 *>(f1g + ((size_t)b * HW1 + q) * C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (lane + 32 * i < nvec) o[lane + 32 * i] = ga[i];
+}
+
+int check_alt(const char *who, int B, int N, int H1, int W1, int H2, int W2, int C, int radius) {
+  B200_CHECK(B >= 0 && N >= 1 && H1 >= 1 && W1 >= 1 && H2 >= 1 && W2 >= 1, "%s: bad sizes", who);
+  B200_CHECK(C >= 4 && C % 4 == 0 && C <= 128 * kMaxVec, "%s: C must be a multiple of 4, <= %d", who,
+             128 * kMaxVec);
+  B200_CHECK(radius >= 1 && radius <= 4, "%s: radius %d not instantiated (1..4)", who, radius);
+  return 0;
+}
+
+#define ALT_DISPATCH(KERNEL, ...)                                                           \
+  do {                                                                                      \
+    const int nv = (C / 4 + 31) / 32;                                                       \
+    switch (radius * 8 + nv) {                                                              \
+      case 1 * 8 + 1: KERNEL<1, 1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+      case 1 * 8 + 2: KERNEL<1, 2><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+      case 1 * 8 + 3: case 1 * 8 + 4: KERNEL<1, 4><<<grid, 256, 0, stream>>>(__VA_ARGS__); break; \
+      case 2 * 8 + 1: KERNEL<2, 1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+      case 2 * 8 + 2: KERNEL<2, 2><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+      case 2 * 8 + 3: case 2 * 8 + 4: KERNEL<2, 4><<<grid, 256, 0, stream>>>(__VA_ARGS__); break; \
+      case 3 * 8 + 1: KERNEL<3, 1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+      case 3 * 8 + 2: KERNEL<3, 2><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+      case 3 * 8 + 3: case 3 * 8 + 4: KERNEL<3, 4><<<grid, 256, 0, stream>>>(__VA_ARGS__); break; \
+      case 4 * 8 + 1: KERNEL<4, 1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+      case 4 * 8 + 2: KERNEL<4, 2><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+      default: KERNEL<4, 4><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;                  \
+    }                                                                                       \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int b200corr_altcorr_forward(const float *fmap1, const float *fmap2, const float *coords,
+                             float *corr, int B, int N, int H1, int W1, int H2, int W2, int C,
+                             int radius, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_alt("altcorr_forward", B, N, H1, W1, H2, W2, C, radius)) return e;
+  if (B == 0) return 0;
+  B200_CHECK(fmap1 && fmap2 && coords && corr, "altcorr_forward: null pointer");
+  B200_CHECK((((uintptr_t)fmap1 | (uintptr_t)fmap2) & 15) == 0, "altcorr_forward: feature maps must be 16-byte aligned");
+  dim3 grid((H1 * W1 + 7) / 8, N, B);
+  ALT_DISPATCH(altcorr_fwd_kernel, fmap1, fmap2, coords, corr, B, N, H1, W1, H2, W2, C);
+  B200_LAUNCH_OK("altcorr_fwd_kernel");
+  return 0;
+}
+
+int b200corr_altcorr_backward(const float *fmap1, const float *fmap2, const float *coords,
+                              const float *corr_grad, float *fmap1_grad, float *fmap2_grad,
+                              float *coords_grad, int B, int N, int H1, int W1, int H2, int W2,
+                              int C, int radius, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_alt("altcorr_backward", B, N, H1, W1, H2, W2, C, radius)) return e;
+  if (B == 0) return 0;
+  B200_CHECK(fmap1 && fmap2 && coords && corr_grad && fmap1_grad && fmap2_grad,
+             "altcorr_backward: null pointer");
+  B200_CHECK((((uintptr_t)fmap1 | (uintptr_t)fmap2 | (uintptr_t)fmap1_grad | (uintptr_t)fmap2_grad) & 15) == 0,
+             "altcorr_backward: feature maps and gradients must be 16-byte aligned");
+  B200_CUDA(cudaMemsetAsync(fmap2_grad, 0, sizeof(float) * (size_t)B * H2 * W2 * C, stream));
+  if (coords_grad)  // the reference allocates zeros and never writes them (correlation_kernel.cu:307)
+    B200_CUDA(cudaMemsetAsync(coords_grad, 0, sizeof(float) * (size_t)B * N * H1 * W1 * 2, stream));
+  dim3 grid((H1 * W1 + 7) / 8, 1, B);
+  ALT_DISPATCH(altcorr_bwd_kernel, fmap1, fmap2, coords, corr_grad, fmap1_grad, fmap2_grad, B, N, H1,
+               W1, H2, W2, C);
+  B200_LAUNCH_OK("altcorr_bwd_kernel");
+  return 0;
+}
+
+}  // extern "C"

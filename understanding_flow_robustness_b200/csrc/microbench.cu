@@ -59,35 +59,60 @@ __global__ void __launch_bounds__(512) lds_probe_kernel(float *sink, int iters, 
   if (a0 == 0x12345u) sink[0] = (float)a0;
 }
 
-// 8 x 21 Toeplitz register update, operands refreshed from registers only.
-__global__ void __launch_bounds__(256, 1) ffma_toeplitz_kernel(float *sink, int iters, float seed) {
-  float acc[8][21];
+// packed FFMA2 peak: 16 independent float2 chains per thread, operands in registers
+__global__ void __launch_bounds__(256) ffma2_peak_kernel(float *sink, int iters, float seed) {
+  float2 acc[16];
 #pragma unroll
-  for (int t = 0; t < 8; ++t)
-#pragma unroll
-    for (int k = 0; k < 21; ++k) acc[t][k] = 0.f;
-  float a[8], v[48];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) a[t] = seed + threadIdx.x + t;
-#pragma unroll
-  for (int m = 0; m < 48; ++m) v[m] = seed * m + 1.f;
+  for (int i = 0; i < 16; ++i) acc[i] = make_float2(seed + threadIdx.x + i, seed - i);
+  const float2 x = make_float2(1.0000001f + seed, 0.9999999f - seed);
+  const float2 y = make_float2(0.5f * seed, 1.f - seed);
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t)
+    for (int u = 0; u < 8; ++u)
 #pragma unroll
-      for (int k = 0; k < 21; ++k) acc[t][k] = fmaf(a[t], v[t + 2 * k], acc[t][k]);
-    // cheap operand refresh so the loop body is not hoisted (8 + 12 non-FMA instructions)
-#pragma unroll
-    for (int t = 0; t < 8; ++t) a[t] = __int_as_float(__float_as_int(a[t]) ^ (it << 3));
-#pragma unroll
-    for (int m = 0; m < 48; m += 4) v[m] = __int_as_float(__float_as_int(v[m]) ^ it);
+      for (int i = 0; i < 16; ++i) acc[i] = __ffma2_rn(acc[i], x, y);
   }
   float s = 0.f;
 #pragma unroll
-  for (int t = 0; t < 8; ++t)
+  for (int i = 0; i < 16; ++i) s += acc[i].x + acc[i].y;
+  if (s == 12345.678f) sink[0] = s;
+}
+
+// register-blocked update of the sampler forward with FFMA2, operands refreshed from shared memory
+// with the real access pattern replaced by a conflict-free broadcast (isolates the FMA pipe)
+__global__ void __launch_bounds__(256, 1) ffma_toeplitz_kernel(float *sink, int iters, float seed) {
+  __shared__ float4 sm[64];
+  if (threadIdx.x < 64) sm[threadIdx.x] = make_float4(seed + threadIdx.x, 1.f, seed, 2.f);
+  __syncthreads();
+  float2 acc[4][21];
 #pragma unroll
-    for (int k = 0; k < 21; ++k) s += acc[t][k];
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int k = 0; k < 21; ++k) acc[t][k] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    const float4 a0 = sm[(it & 3)], a1 = sm[(it & 3) + 4];
+    const float2 ap[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
+                          make_float2(a1.z, a1.w)};
+#pragma unroll
+    for (int sg = 0; sg < 12; ++sg) {
+      const float4 v4 = sm[8 + sg + (it & 3) * 12];
+      const float2 vp[2] = {make_float2(v4.x, v4.y), make_float2(v4.z, v4.w)};
+#pragma unroll
+      for (int uu = 0; uu < 2; ++uu)
+#pragma unroll
+        for (int tp = 0; tp < 4; ++tp) {
+          const int d = 2 * sg + uu - tp;
+          if (d >= 0 && d < 21) acc[tp][d] = __ffma2_rn(ap[tp], vp[uu], acc[tp][d]);
+        }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int k = 0; k < 21; ++k) s += acc[t][k].x + acc[t][k].y;
   if (s == 12345.678f) sink[0] = s;
 }
 
@@ -119,6 +144,35 @@ int b200corr_probe_lds(int pattern, int warps, int iters, float *cycles_per_lds,
   *cycles_per_lds = (float)(sum / n / ((double)iters * 16 * warps));
   cudaFree(sink);
   cudaFree(cyc);
+  return 0;
+}
+
+// achieved TFLOP/s of back-to-back packed FFMA2 (2 FMAs per lane per instruction)
+int b200corr_probe_ffma2_peak(int iters, float *tflops, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK(iters > 0 && tflops, "probe_ffma2_peak: bad arguments");
+  float *sink = nullptr;
+  B200_CUDA(cudaMalloc(&sink, sizeof(float)));
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0));
+  B200_CUDA(cudaEventCreate(&e1));
+  const int blocks = b200::num_sms() * 8;
+  ffma2_peak_kernel<<<blocks, 256, 0, stream>>>(sink, 8, 0.f);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    B200_CUDA(cudaEventRecord(e0, stream));
+    ffma2_peak_kernel<<<blocks, 256, 0, stream>>>(sink, iters, 0.f);
+    B200_CUDA(cudaEventRecord(e1, stream));
+    B200_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  B200_LAUNCH_OK("ffma2_peak_kernel");
+  *tflops = (float)(2.0 * 2 * 16 * 8 * (double)iters * blocks * 256 / (best * 1e-3) / 1e12);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
   return 0;
 }
 

@@ -65,22 +65,23 @@ struct FwdParams {
   b200::SamplerGroups g;
 };
 
-// Displacement range and unit split of one row group (same arithmetic on host and device).
+// in2 sub-row range [Rlo, Rlo + nR) a row group needs, and its split into units of <= SLOTS items
+// (item = (column group, in2 sub-row)); same arithmetic on host and device.
 __host__ __device__ inline void fwd_group_geom(int NS, int s0, int RH, int NG, int GMAX, int SLOTS,
-                                               int &e_lo, int &ne, int &nch, int &cs) {
+                                               int &Rlo, int &nR, int &nch, int &cs) {
   const int s_last = (s0 + b200::kRowsPerGroup - 1 < NS - 1) ? s0 + b200::kRowsPerGroup - 1 : NS - 1;
-  e_lo = -RH > -s_last ? -RH : -s_last;
-  const int e_hi = RH < NS - 1 - s0 ? RH : NS - 1 - s0;
-  ne = e_hi - e_lo + 1;
-  const int nitems = NG * ne;
-  int cap = (GMAX - 1) * ne;
+  Rlo = s0 - RH > 0 ? s0 - RH : 0;
+  const int Rhi = s_last + RH < NS - 1 ? s_last + RH : NS - 1;
+  nR = Rhi - Rlo + 1;
+  const int nitems = NG * nR;
+  int cap = (GMAX - 1) * nR;
   if (cap > SLOTS) cap = SLOTS;
   nch = (nitems + cap - 1) / cap;
   cs = (nitems + nch - 1) / nch;
 }
 
 struct Unit {
-  int n, rp, s0, NS, e_lo, ne, item0, cnt, g0;
+  int n, rp, s0, NS, Rlo, nR, item0, cnt, g0;
 };
 
 template <class Cfg>
@@ -93,12 +94,12 @@ __device__ __forceinline__ void decode_unit(const FwdParams &p, int u, Unit &x) 
   x.s0 = p.g.s0[gi];
   x.NS = (p.H - x.rp + p.dpH - 1) / p.dpH;
   int nch, cs;
-  fwd_group_geom(x.NS, x.s0, Cfg::RH, p.NG, Cfg::GMAX, Cfg::SLOTS, x.e_lo, x.ne, nch, cs);
+  fwd_group_geom(x.NS, x.s0, Cfg::RH, p.NG, Cfg::GMAX, Cfg::SLOTS, x.Rlo, x.nR, nch, cs);
   const int k = r - p.g.prefix[gi];
   x.item0 = k * cs;
-  const int nitems = p.NG * x.ne;
+  const int nitems = p.NG * x.nR;
   x.cnt = nitems - x.item0 < cs ? nitems - x.item0 : cs;
-  x.g0 = x.item0 / x.ne;
+  x.g0 = x.item0 / x.nR;
 }
 
 __device__ __forceinline__ void stg128(float *p, float a, float b, float c, float d) {
@@ -117,12 +118,14 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
   Unit &px = *reinterpret_cast<Unit *>(empty_bar + NST);  // producer-side unit (thread 0 only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // Lane layout (measured on B200, scripts/probe_sm.py: an LDS.128 costs max(2, runs/8) cycles where
-  // a "run" is a maximal group of ADJACENT lanes reading the same 16 bytes -- sharing between
-  // non-adjacent lanes is not merged).  The 4 lanes of a quad are the 4 pixel rows; quad q takes
-  // item (q - li) mod 8, so lanes of a quad that read the same in2 row (li + e constant) are adjacent.
-  const int li = lane & 3;                  // pixel row inside the group (0..3)
-  const int lj = ((lane >> 2) - li) & 7;    // item column inside the warp (0..7)
+  // Lane layout.  Measured on B200 (scripts/probe_sm.py + ncu wavefront counters): an LDS.128
+  // returns 8 sixteen-byte slots per wavefront and only an aligned lane PAIR (2i, 2i+1) that reads
+  // the same 16 bytes shares a slot; sharing between other lanes is not merged.  So the 4 pixel-row
+  // lanes of an item are adjacent (li fastest) and all read the SAME in2 row: an item is
+  // (column group, in2 sub-row R) and lane li handles the displacement e = R - s(li).  One in2
+  // LDS.128 then costs 2 wavefronts instead of 4.
+  const int li = lane & 3;   // pixel row inside the group (0..3)
+  const int lj = lane >> 2;  // item inside the warp (0..7)
 
   if (tid == 0) {
     tma_prefetch_desc(&map1);
@@ -149,7 +152,7 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
     mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
     const int ch = px.n * p.C + pc * CC;
     tma_load_3d(dst, &map2, &full_bar[st], px.g0 * Cfg::T - Cfg::HALO,
-                (px.s0 + px.e_lo) * p.dpH + px.rp, ch);
+                px.Rlo * p.dpH + px.rp, ch);
     tma_load_3d(dst + Cfg::IN2_FLOATS, &map1, &full_bar[st], px.g0 * Cfg::T,
                 px.s0 * p.dpH + px.rp, ch);
     ++pq;
@@ -169,10 +172,11 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
     const int slot = warp * 8 + lj;
     const bool active = slot < x.cnt;
     const int item = x.item0 + (active ? slot : 0);
-    const int g = item / x.ne;
-    const int e = x.e_lo + (item - g * x.ne);
+    const int g = item / x.nR;
+    const int rbox = item - g * x.nR;          // in2 row inside the staged box
     const int s = x.s0 + li;
-    const int rbox = li + (e - x.e_lo);        // in2 row inside the staged box
+    const int e = x.Rlo + rbox - s;            // row displacement this lane computes
+    const bool valid = active && s < x.NS && e >= -Cfg::RH && e <= Cfg::RH;
     const int cb = (g - x.g0) * Cfg::T;        // column offset inside both boxes
     const int off2 = rbox * NC2 + cb;
     const int off1 = Cfg::IN2_FLOATS + li * NC1 + cb;
@@ -241,7 +245,7 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
     }
 
     // ---- epilogue: every (n, ph, pw, h, w) of this unit's rows/columns is written exactly once
-    if (active && s < x.NS) {
+    if (valid) {
       const size_t HW = (size_t)p.H * p.W;
       const int h = s * p.dpH + x.rp;
       const int w0 = g * Cfg::T;
@@ -252,11 +256,13 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
         if (lo_ok) stg128(o + k * HW, acc2[0][k].x, acc2[0][k].y, acc2[1][k].x, acc2[1][k].y);
         if (hi_ok) stg128(o + k * HW + 4, acc2[2][k].x, acc2[2][k].y, acc2[3][k].x, acc2[3][k].y);
       }
-      // row displacements clipped away for the whole group: zero planes
-      const int nclip = PH - x.ne;
-      const int below = x.e_lo + Cfg::RH;  // clipped planes [0, below) and [below + ne, PH)
-      for (int qq = e - x.e_lo; qq < nclip; qq += x.ne) {
-        const int phc = qq < below ? qq : qq + x.ne;
+      // displacement planes whose in2 row lies outside the image are zero; the valid lanes of this
+      // pixel row share them out by their rank among the valid rows
+      const int below = Cfg::RH - s > 0 ? Cfg::RH - s : 0;                      // planes [0, below)
+      const int above = Cfg::RH - (x.NS - 1 - s) > 0 ? Cfg::RH - (x.NS - 1 - s) : 0;  // [PH-above, PH)
+      const int nvalid = PH - below - above;
+      for (int qq = e + Cfg::RH - below; qq < below + above; qq += nvalid) {
+        const int phc = qq < below ? qq : PH - above + (qq - below);
         float *z = out + (((size_t)x.n * PH + phc) * PW) * HW + (size_t)h * p.W + w0;
         for (int k = 0; k < PW; ++k) {
           if (lo_ok) stg128(z + k * HW, 0.f, 0.f, 0.f, 0.f);
@@ -278,8 +284,8 @@ int launch_fwd(const float *in1, const float *in2, float *out, int B, int C, int
     const int NS = b200::sublattice_rows(H, dpH, rp);
     for (int s0 = 0; s0 < NS; s0 += b200::kRowsPerGroup) {
       B200_CHECK(ng < b200::kSamplerMaxGroups, "sampler_fast_forward: too many row groups");
-      int e_lo, ne, nch, cs;
-      fwd_group_geom(NS, s0, Cfg::RH, p.NG, Cfg::GMAX, Cfg::SLOTS, e_lo, ne, nch, cs);
+      int Rlo, nR, nch, cs;
+      fwd_group_geom(NS, s0, Cfg::RH, p.NG, Cfg::GMAX, Cfg::SLOTS, Rlo, nR, nch, cs);
       p.g.prefix[ng] = units;
       p.g.rp[ng] = (short)rp;
       p.g.s0[ng] = (short)s0;

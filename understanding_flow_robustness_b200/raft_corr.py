@@ -1,0 +1,338 @@
+"""RAFT correlation blocks on the B200 kernels: `CorrBlock`, `AlternateCorrBlock`, `alt_cuda_corr`.
+
+Mirrors models/raft/corr.py of the reference (same constructor / call signatures, same output
+layout and channel order) and the pybind surface of models/alt_cuda_corr/correlation.cpp:51-54.
+
+  CorrBlock(fmap1, fmap2, num_levels=4, radius=4, compute_spatial=False)(coords) -> (B, L*(2r+1)^2, H, W)
+      reference: corr.py:26-106.  The all-pairs volume, its 1/sqrt(C) scale and the pooled pyramid
+      come out of one tcgen05 kernel; every lookup is one gather kernel for all levels.
+  AlternateCorrBlock(fmap1, fmap2, num_levels=4, radius=4)(coords)
+      reference: corr.py:109-137.  Same result without materialising the volume.
+  alt_cuda_corr.forward(fmap1, fmap2, coords, radius) -> [corr]
+  alt_cuda_corr.backward(fmap1, fmap2, coords, corr_grad, radius) -> [fmap1_grad, fmap2_grad, coords_grad]
+
+Differences from the reference, all deliberate:
+  * the volume is computed from TF32-rounded features by default (`precision="tf32"`; bound in
+    DESIGN.md); `precision="fp32"` selects the exact CUDA-core kernel;
+  * both blocks are differentiable w.r.t. the feature maps (the reference's AlternateCorrBlock is
+    forward-only because nothing wraps alt_cuda_corr.backward); coordinates get no gradient, as in
+    the reference (raft.py:188 detaches them, correlation_kernel.cu:307 returns zeros);
+  * lookups accumulate their gradient in place into ONE dense gradient pyramid per block instead of
+    allocating a dense volume gradient per grid_sample call.
+"""
+import math
+import types
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .spatial_correlation_sampler import spatial_correlation_sample
+
+PRECISIONS = {"tf32": 0, "fp32": 2}
+LOOKUP_MODES = {"grid_sample": 0, "direct": 1}
+
+
+def coords_grid(batch, ht, wd, device=None):
+    """models/raft/utils/utils.py:79-82 -- (B, 2, H, W), channel 0 = x."""
+    ys, xs = torch.meshgrid(torch.arange(ht, device=device), torch.arange(wd, device=device), indexing="ij")
+    return torch.stack([xs, ys], dim=0).float()[None].repeat(batch, 1, 1, 1)
+
+
+def bilinear_sampler(img, coords, mask=False):
+    """models/raft/utils/utils.py:62-76 (kept for callers that import it from the corr module)."""
+    H, W = img.shape[-2:]
+    xgrid, ygrid = coords.split([1, 1], dim=-1)
+    xgrid = 2 * xgrid / (W - 1) - 1
+    ygrid = 2 * ygrid / (H - 1) - 1
+    grid = torch.cat([xgrid, ygrid], dim=-1)
+    img = F.grid_sample(img, grid, align_corners=True)
+    if mask:
+        m = (xgrid > -1) & (ygrid > -1) & (xgrid < 1) & (ygrid < 1)
+        return img, m.float()
+    return img
+
+
+def _require_cuda_f32(who, *ts):
+    for t in ts:
+        if not t.is_cuda:
+            raise RuntimeError(f"{who}: CUDA tensors required (this build has no CPU path)")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"{who}: float32 tensors required, got {t.dtype}")
+        if t.device != ts[0].device:
+            raise RuntimeError(f"{who}: tensors must be on the same device")
+
+
+def _level_shapes(H, W, num_levels):
+    shapes = []
+    for _ in range(num_levels):
+        shapes.append((H, W))
+        H, W = H // 2, W // 2
+    return shapes
+
+
+# ------------------------------------------------------------------------------------------------
+# raw C-ABI calls
+def allpairs_pyramid(fmap1, fmap2, num_levels=4, precision="tf32"):
+    """List of (B*H*W, 1, H_l, W_l) tensors: vol_0 = f1^T f2 / sqrt(C), vol_{l+1} = avg_pool2d(vol_l, 2, 2)."""
+    fmap1 = fmap1.contiguous()
+    fmap2 = fmap2.contiguous()
+    _require_cuda_f32("allpairs_pyramid", fmap1, fmap2)
+    if fmap1.shape != fmap2.shape or fmap1.dim() != 4:
+        raise RuntimeError("allpairs_pyramid: fmap1 and fmap2 must both be (B, C, H, W) of the same shape")
+    B, C, H, W = fmap1.shape
+    prec = PRECISIONS[precision]
+    L = _lib.lib()
+    levels = [torch.empty((B * H * W, 1, h, w), dtype=torch.float32, device=fmap1.device)
+              for (h, w) in _level_shapes(H, W, num_levels)]
+    nbytes = L.b200corr_allpairs_workspace_bytes(B, C, H, W, prec)
+    ws = torch.empty((max(nbytes, 1) + 127) // 128 * 32, dtype=torch.float32, device=fmap1.device)
+    with torch.cuda.device(fmap1.device):
+        code = L.b200corr_allpairs_pyramid(_lib.ptr(fmap1), _lib.ptr(fmap2), _lib.ptr_array(levels), num_levels,
+                                           B, C, H, W, 1.0 / math.sqrt(C), prec, _lib.ptr(ws), nbytes,
+                                           _lib.current_stream(fmap1.device))
+    _lib.check(code, "b200corr_allpairs_pyramid")
+    return levels
+
+
+def lookup_forward(levels, coords, radius, H, W, mode="grid_sample"):
+    coords = coords.contiguous()
+    _require_cuda_f32("lookup_forward", coords, *levels)
+    B = coords.shape[0]
+    n = (2 * radius + 1) ** 2
+    out = torch.empty((B, len(levels) * n, H, W), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        code = _lib.lib().b200corr_lookup_forward(_lib.ptr_array(levels), len(levels), _lib.ptr(coords),
+                                                  _lib.ptr(out), B, H, W, radius, LOOKUP_MODES[mode],
+                                                  _lib.current_stream(coords.device))
+    _lib.check(code, "b200corr_lookup_forward")
+    return out
+
+
+def lookup_backward(grad_levels, coords, grad_out, radius, H, W, mode="grid_sample"):
+    coords = coords.contiguous()
+    grad_out = grad_out.contiguous()
+    _require_cuda_f32("lookup_backward", coords, grad_out, *grad_levels)
+    B = coords.shape[0]
+    with torch.cuda.device(coords.device):
+        code = _lib.lib().b200corr_lookup_backward(_lib.ptr_array(grad_levels), len(grad_levels),
+                                                   _lib.ptr(coords), _lib.ptr(grad_out), B, H, W, radius,
+                                                   LOOKUP_MODES[mode], _lib.current_stream(coords.device))
+    _lib.check(code, "b200corr_lookup_backward")
+
+
+def pyramid_backward(grad_levels, B, H, W):
+    with torch.cuda.device(grad_levels[0].device):
+        code = _lib.lib().b200corr_pyramid_backward(_lib.ptr_array(grad_levels), len(grad_levels), B, H, W,
+                                                    _lib.current_stream(grad_levels[0].device))
+    _lib.check(code, "b200corr_pyramid_backward")
+
+
+# ------------------------------------------------------------------------------------------------
+# alt_cuda_corr drop-in (models/alt_cuda_corr/correlation.cpp:23-54)
+def _alt_check(fmap1, fmap2, coords):
+    for t in (fmap1, fmap2, coords):
+        if not t.is_cuda:
+            raise RuntimeError("alt_cuda_corr: must be a CUDA tensor")          # CHECK_CUDA
+        if not t.is_contiguous():
+            raise RuntimeError("alt_cuda_corr: must be contiguous")             # CHECK_CONTIGUOUS
+    _require_cuda_f32("alt_cuda_corr", fmap1, fmap2, coords)
+    if fmap1.dim() != 4 or fmap2.dim() != 4 or coords.dim() != 5 or coords.shape[-1] != 2:
+        raise RuntimeError("alt_cuda_corr: expected fmap (B,H,W,C) and coords (B,N,H,W,2)")
+    if fmap1.shape[0] != fmap2.shape[0] or fmap1.shape[3] != fmap2.shape[3]:
+        raise RuntimeError("alt_cuda_corr: batch / channel mismatch between the feature maps")
+    if coords.shape[0] != fmap1.shape[0] or tuple(coords.shape[2:4]) != tuple(fmap1.shape[1:3]):
+        raise RuntimeError("alt_cuda_corr: coords must be (B, N, H1, W1, 2)")
+
+
+def _alt_forward(fmap1, fmap2, coords, radius):
+    _alt_check(fmap1, fmap2, coords)
+    B, H1, W1, C = fmap1.shape
+    _, H2, W2, _ = fmap2.shape
+    N = coords.shape[1]
+    rd = 2 * radius + 1
+    corr = torch.empty((B, N, rd * rd, H1, W1), dtype=torch.float32, device=fmap1.device)
+    with torch.cuda.device(fmap1.device):
+        code = _lib.lib().b200corr_altcorr_forward(_lib.ptr(fmap1), _lib.ptr(fmap2), _lib.ptr(coords),
+                                                   _lib.ptr(corr), B, N, H1, W1, H2, W2, C, radius,
+                                                   _lib.current_stream(fmap1.device))
+    _lib.check(code, "b200corr_altcorr_forward")
+    return [corr]
+
+
+def _alt_backward(fmap1, fmap2, coords, corr_grad, radius):
+    _alt_check(fmap1, fmap2, coords)
+    corr_grad = corr_grad.contiguous()
+    B, H1, W1, C = fmap1.shape
+    _, H2, W2, _ = fmap2.shape
+    N = coords.shape[1]
+    g1 = torch.empty_like(fmap1)
+    g2 = torch.empty_like(fmap2)
+    gc = torch.empty_like(coords)
+    with torch.cuda.device(fmap1.device):
+        code = _lib.lib().b200corr_altcorr_backward(_lib.ptr(fmap1), _lib.ptr(fmap2), _lib.ptr(coords),
+                                                    _lib.ptr(corr_grad), _lib.ptr(g1), _lib.ptr(g2),
+                                                    _lib.ptr(gc), B, N, H1, W1, H2, W2, C, radius,
+                                                    _lib.current_stream(fmap1.device))
+    _lib.check(code, "b200corr_altcorr_backward")
+    return [g1, g2, gc]
+
+
+alt_cuda_corr = types.ModuleType("alt_cuda_corr")
+alt_cuda_corr.__doc__ = "B200 drop-in for the reference's alt_cuda_corr extension (forward / backward)."
+alt_cuda_corr.forward = _alt_forward
+alt_cuda_corr.backward = _alt_backward
+
+
+class _AltCorrFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, coords, radius):
+        ctx.save_for_backward(fmap1, fmap2, coords)
+        ctx.radius = radius
+        return _alt_forward(fmap1, fmap2, coords, radius)[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        fmap1, fmap2, coords = ctx.saved_tensors
+        g1, g2, _ = _alt_backward(fmap1, fmap2, coords, grad, ctx.radius)
+        return g1, g2, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+class _VolumeFunction(torch.autograd.Function):
+    """Builds the pyramid into `block` and returns a 1-element handle that carries the autograd edge
+    from the lookups back to the feature maps."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, block):
+        block.corr_pyramid = allpairs_pyramid(fmap1, fmap2, block.num_levels, block.precision)
+        ctx.save_for_backward(fmap1, fmap2)
+        ctx.block = block
+        return fmap1.new_zeros(1)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _grad_handle):
+        fmap1, fmap2 = ctx.saved_tensors
+        block = ctx.block
+        B, C, H, W = fmap1.shape
+        gl = block._grad_levels
+        block._grad_levels = None
+        if gl is None:
+            return torch.zeros_like(fmap1), torch.zeros_like(fmap2), None
+        pyramid_backward(gl, B, H, W)
+        gvol = gl[0].view(B, H * W, H * W)
+        scale = 1.0 / math.sqrt(C)
+        # plain library GEMMs (cuBLAS): dF1 = scale * F2 gvol^T, dF2 = scale * F1 gvol
+        g1 = torch.bmm(fmap2.reshape(B, C, H * W), gvol.transpose(1, 2)).mul_(scale).view_as(fmap1)
+        g2 = torch.bmm(fmap1.reshape(B, C, H * W), gvol).mul_(scale).view_as(fmap2)
+        return g1, g2, None
+
+
+class _LookupFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, handle, coords, block):
+        ctx.block = block
+        ctx.save_for_backward(coords)
+        return lookup_forward(block.corr_pyramid, coords, block.radius, block.H, block.W, block.lookup_mode)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        (coords,) = ctx.saved_tensors
+        block = ctx.block
+        if block._grad_levels is None:
+            block._grad_levels = [torch.zeros_like(v) for v in block.corr_pyramid]
+        lookup_backward(block._grad_levels, coords, grad_out, block.radius, block.H, block.W, block.lookup_mode)
+        return grad_out.new_zeros(1), None, None
+
+
+class CorrBlock:
+    """models/raft/corr.py:26-106."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, compute_spatial=False, precision="tf32",
+                 lookup_mode="grid_sample"):
+        self.num_levels = num_levels
+        self.radius = radius
+        self.compute_spatial = compute_spatial
+        self.precision = precision
+        self.lookup_mode = lookup_mode
+        self.corr_pyramid = []
+        self._grad_levels = None
+        self._handle = None
+        if self.compute_spatial:
+            # corr.py:33-54: FlowNetC-style 21x21 (dilation 2) correlation instead of all pairs
+            self.upsample = torch.nn.Upsample(scale_factor=2, mode="nearest")
+            out_corr = spatial_correlation_sample(fmap1, fmap2, kernel_size=1, patch_size=21, stride=1,
+                                                  padding=0, dilation_patch=2)
+            batch, ph, pw, h, w = out_corr.size()
+            self.spatial_corr = out_corr.view(batch, ph * pw, h, w) / fmap1.size(1)
+            corr = out_corr.view(batch * ph * pw, 1, h, w)
+            self.corr_pyramid.append(corr)
+            for _ in range(self.num_levels - 1):
+                corr = F.avg_pool2d(corr, 2, stride=2)
+                self.corr_pyramid.append(corr)
+        else:
+            self.B, self.C, self.H, self.W = fmap1.shape
+            needs_grad = torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad)
+            if needs_grad:
+                self._handle = _VolumeFunction.apply(fmap1.contiguous(), fmap2.contiguous(), self)
+            else:
+                self.corr_pyramid = allpairs_pyramid(fmap1.detach(), fmap2.detach(), num_levels, precision)
+
+    def get_corr_pyramid(self):
+        return self.corr_pyramid
+
+    def get_spatial_corr(self):
+        return self.spatial_corr if self.compute_spatial else None
+
+    def __call__(self, coords):
+        if self.compute_spatial:
+            # corr.py:88-93: the pooled sampler outputs are upsampled back, coords are ignored
+            batch, _, h1, w1 = coords.shape
+            out_pyramid = []
+            for i in range(self.num_levels):
+                corr = self.corr_pyramid[i]
+                for _ in range(i):
+                    corr = self.upsample(corr)
+                out_pyramid.append(corr.view(batch, h1, w1, -1))
+            return torch.cat(out_pyramid, dim=-1).permute(0, 3, 1, 2).contiguous().float()
+        coords = coords.detach().float()
+        if self._handle is not None and torch.is_grad_enabled():
+            return _LookupFunction.apply(self._handle, coords, self)
+        return lookup_forward(self.corr_pyramid, coords, self.radius, self.H, self.W, self.lookup_mode)
+
+    @staticmethod
+    def corr(fmap1, fmap2, precision="tf32"):
+        """corr.py:98-106 -> (B, H, W, 1, H, W)."""
+        B, C, H, W = fmap1.shape
+        return allpairs_pyramid(fmap1, fmap2, 1, precision)[0].view(B, H, W, 1, H, W)
+
+
+class AlternateCorrBlock:
+    """models/raft/corr.py:109-137.  The NHWC copies are made once here instead of on every call."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+        self.num_levels = num_levels
+        self.radius = radius
+        self.pyramid = [(fmap1, fmap2)]
+        for _ in range(self.num_levels):
+            fmap1 = F.avg_pool2d(fmap1, 2, stride=2)
+            fmap2 = F.avg_pool2d(fmap2, 2, stride=2)
+            self.pyramid.append((fmap1, fmap2))
+        self._f1 = self.pyramid[0][0].permute(0, 2, 3, 1).contiguous().float()
+        self._f2 = [self.pyramid[i][1].permute(0, 2, 3, 1).contiguous().float() for i in range(num_levels)]
+
+    def __call__(self, coords):
+        coords = coords.permute(0, 2, 3, 1)
+        B, H, W, _ = coords.shape
+        dim = self.pyramid[0][0].shape[1]
+        corr_list = []
+        for i in range(self.num_levels):
+            coords_i = (coords / 2 ** i).reshape(B, 1, H, W, 2).contiguous().float().detach()
+            corr = _AltCorrFunction.apply(self._f1, self._f2[i], coords_i, self.radius)
+            corr_list.append(corr.squeeze(1))
+        corr = torch.stack(corr_list, dim=1)
+        corr = corr.reshape(B, -1, H, W)
+        return corr / math.sqrt(dim)
