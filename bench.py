@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-raft", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-attack", action="store_true")
+    ap.add_argument("--attack-batch", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -289,6 +291,12 @@ def main():
     h2d = (h_in1.numel() + h_in2.numel() + h_gout.numel()) * 4
     d2h = (h_out.numel() + h_g1.numel() + h_g2.numel()) * 4
 
+    attack_res = None
+    if not args.no_attack:
+        del h_in1, h_in2, h_gout, h_out, h_g1, h_g2, d1, d2, dg
+        torch.cuda.empty_cache()
+        attack_res = attack_bench(dev, rank, world, args.attack_batch)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -325,6 +333,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "roofline": roofline}
 
+    if attack_res is not None:
+        line["attack"] = attack_res
     if not args.no_raft:
         line["raft"] = raft_bench(dev)
     if not args.no_cpu_baseline:
@@ -337,6 +347,59 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def attack_bench(dev, rank, world, global_batch):
+    """BASELINE config 4: universal 100x100 patch attack on the FlowNetC harness (random init), global
+    batch of 384x1280 pairs sharded r::G over the ranks, patch gradient all-reduced (NCCL) every inner
+    step.  Strong scaling: the global batch is fixed.  iteration = clean forward + max_count x
+    (forward + backward) + all-reduce + update."""
+    import torch
+    import torch.distributed as dist
+
+    from understanding_flow_robustness_b200 import attack
+    from understanding_flow_robustness_b200.harness import FlowNetCHarness
+    torch.manual_seed(0)                                   # same weights / patch on every rank
+    net = FlowNetCHarness().to(dev).eval()
+    for q in net.parameters():
+        q.requires_grad_(False)
+    H, W, p = 384, 1280, 100
+    idx = attack.shard_slice(global_batch, rank, world)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    i1 = torch.rand(len(idx), 3, H, W, device=dev, generator=g)
+    i2 = torch.rand(len(idx), 3, H, W, device=dev, generator=g)
+    patch = torch.rand(1, 3, p, p, device=dev)
+    mask = attack.circle_mask(p, dev)
+    cfg = attack.PatchAttackConfig()
+    init = patch.clone()
+
+    def it(pt):
+        return attack.patch_attack_iteration(net, i1, i2, pt, mask, init, cfg, global_batch, g)[0]
+
+    patch = it(patch)                                      # warm-up (cuDNN autotune, allocator)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    iters = 3
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        patch = it(patch)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / iters
+    return {"metric": "patch-attack iters/s", "value": 1e3 / ms, "unit": "iters/s", "ms_per_iter": ms,
+            "pairs_per_s": global_batch * 1e3 / ms, "scaling": "strong", "global_batch": global_batch,
+            "pairs_per_rank": len(idx), "n_gpus": world,
+            "config": "FlowNetC harness (random init) 384x1280, 100x100 circular patch, max_count 2, cosine loss, "
+                      "patch-gradient all-reduce (NCCL) per inner step",
+            "allreduce_bytes": int(patch.numel() * 4 + 4)}
 
 
 def raft_bench(dev):
@@ -366,6 +429,7 @@ def raft_bench(dev):
     blk = [None]
 
     def build():
+        blk[0] = None   # RAFT holds one block per forward: the previous 1.25 GB pyramid is released first
         blk[0] = CorrBlock(f1, f2, c["levels"], c["radius"])
 
     def lookups():
