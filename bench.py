@@ -56,7 +56,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -65,6 +65,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append((time.perf_counter(), line.strip()))
+
+    def wait_first_sample(self, timeout=8.0):
+        """NVML start-up holds the driver lock for a while: never let it fall into a timed region."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
 
     def stop(self, t0, t1):
         if self.proc is None:
@@ -86,7 +92,7 @@ class ClockSampler:
                     reasons.add(name)
         mhz.sort()
         return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(mhz)}
+                "samples": len(mhz), "window_s": round(t1 - t0, 3)}
 
 
 # ---------------------------------------------------------------------------- reference CPU arm
@@ -177,7 +183,7 @@ def workload_config(n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-raft", action="store_true")
@@ -218,13 +224,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-        time.sleep(0.25)
+        clocks.wait_first_sample()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     # ---- timed region: K steps, per-kernel-group events on the launching (current) stream
     n0 = L.b200corr_launch_count()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -243,6 +249,13 @@ def main():
     barrier()
     t_wall1 = time.perf_counter()
     launches = L.b200corr_launch_count() - n0
+    # the clock record needs a few 200 ms samples under this load: keep the same step loop running
+    # (untimed) until the sampled window is >= 0.7 s
+    while time.perf_counter() - t_wall0 < 0.7:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
     ms_total = e_start.elapsed_time(e_end)
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps

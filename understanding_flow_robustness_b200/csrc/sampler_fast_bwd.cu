@@ -324,7 +324,11 @@ int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, 
       return e;
   }
   auto kern = sampler_bwd_kernel<Cfg>;
-  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  static bool attr_done = false;  // one process per GPU: set once, not on every launch
+  if (!attr_done) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
   const int grid = p.total_units < b200::num_sms() ? p.total_units : b200::num_sms();
   kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(map_o, map_g, gin, p);
   B200_LAUNCH_OK(Cfg::WHICH == 1 ? "sampler_bwd_kernel<gIn1>" : "sampler_bwd_kernel<gIn2>");

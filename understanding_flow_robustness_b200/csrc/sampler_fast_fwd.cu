@@ -316,7 +316,7 @@ int launch_fwd(const float *in1, const float *in2, float *out, int B, int C, int
     return e;
 
   auto kern = sampler_fwd_kernel<Cfg>;
-  static bool attr_done = false;
+  static bool attr_done = false;  // one process per GPU: set once, not on every launch
   if (!attr_done) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
