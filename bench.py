@@ -318,7 +318,7 @@ def main():
     # ---- roofline of the dominant kernel (sampler_bwd_kernel: two launches per step)
     import ctypes
     pk = ctypes.c_float()
-    _lib.check(L.b200corr_measure_fp32_peak(20000, ctypes.byref(pk), _lib.current_stream(dev)), "fp32 peak")
+    _lib.check(L.b200corr_measure_fp32_peak(4000, ctypes.byref(pk), _lib.current_stream(dev)), "fp32 peak")
     peak = float(pk.value)
     macs = inbounds_macs_per_pair(C, H, W, P, CFG["dilation_patch"])
     flop_launch = 2.0 * macs * B                      # one gradient (or the forward): in-bounds FLOPs
