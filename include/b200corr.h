@@ -77,6 +77,18 @@ size_t b200corr_sampler_backward_workspace_bytes(int B, int C, int H, int W, int
                                                  int dilationH, int dilationW, int dilation_patchH,
                                                  int dilation_patchW, int dH, int dW, int dtype);
 
+/* Backward schedule (host only, no GPU needed): fills `h_plan` (HOST memory, at least
+ * b200corr_sampler_backward_workspace_bytes() bytes) with a longest-processing-time-first
+ * assignment of the backward work units to the persistent CTAs.  The caller copies it to the device
+ * once per problem shape and passes that copy as `workspace` to b200corr_sampler_backward; without
+ * it the kernels fall back to a static round-robin (same results, ~10% slower on ragged work).
+ * The reference has no counterpart (it launches one kernel per batch sample,
+ * correlation_cuda_kernel.cu:305-323). */
+int b200corr_sampler_backward_plan(int B, int C, int H, int W, int kH, int kW, int patchH,
+                                   int patchW, int padH, int padW, int dilationH, int dilationW,
+                                   int dilation_patchH, int dilation_patchW, int dH, int dW,
+                                   int dtype, void *h_plan, size_t bytes);
+
 /* out[B, patchH, patchW, oH, oW] = sum_{c,i,j} in1[b,c,y1,x1] * in2[b,c,y1+dy,x1+dx]
  * (SURVEY.md section 8(0) S1).  Every element of `out` is written.  The 12 integers are in the
  * order of the reference's backend.forward(...) call (spatial_correlation_sampler.py:68-83). */

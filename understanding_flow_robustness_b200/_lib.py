@@ -19,6 +19,7 @@ PROTOTYPES = {
     "b200corr_sampler_forward": (c_int, [c_void_p] * 4 + [c_size_t] + [c_int] * 17 + [c_void_p]),
     "b200corr_sampler_backward": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 17 + [c_void_p]),
     "b200corr_sampler_uses_fast_path": (c_int, [c_int] * 18),
+    "b200corr_sampler_backward_plan": (c_int, [c_int] * 17 + [c_void_p, c_size_t]),
     "b200corr_allpairs_workspace_bytes": (c_size_t, [c_int] * 5),
     "b200corr_allpairs_pyramid": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int,
                                           c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),

@@ -58,6 +58,29 @@ def forward(input1, input2, kH, kW, patchH, patchW, padH, padW, dilationH, dilat
     return out
 
 
+_PLANS = {}
+
+
+def _backward_plan(device, B, C, H, W, hyper, dt):
+    """Device copy of the library's backward schedule, built once per (device, problem shape)."""
+    key = (device, B, C, H, W, hyper, dt)
+    plan = _PLANS.get(key)
+    if plan is None:
+        L = _lib.lib()
+        nbytes = L.b200corr_sampler_backward_workspace_bytes(B, C, H, W, *hyper, dt)
+        if nbytes == 0:
+            plan = False
+        else:
+            host = torch.empty(nbytes // 4, dtype=torch.int32)
+            _lib.check(L.b200corr_sampler_backward_plan(B, C, H, W, *hyper, dt, host.data_ptr(), nbytes),
+                       "b200corr_sampler_backward_plan")
+            plan = host.to(device)
+        if len(_PLANS) > 64:
+            _PLANS.clear()
+        _PLANS[key] = plan
+    return plan
+
+
 def backward(input1, input2, grad_output, kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
              dilation_patchH, dilation_patchW, dH, dW):
     grad_output = grad_output.contiguous()
@@ -70,10 +93,13 @@ def backward(input1, input2, grad_output, kH, kW, patchH, patchW, padH, padW, di
                            f"{(B, patchH, patchW, oH, oW)}")
     g1 = torch.empty_like(input1)
     g2 = torch.empty_like(input2)
+    hyper = (kH, kW, patchH, patchW, padH, padW, dilationH, dilationW, dilation_patchH, dilation_patchW, dH, dW)
     with torch.cuda.device(input1.device):
+        plan = _backward_plan(input1.device, B, C, H, W, hyper, dt)
+        ws, ws_bytes = (_lib.ptr(plan), plan.numel() * 4) if plan is not False else (None, 0)
         code = _lib.lib().b200corr_sampler_backward(
             _lib.ptr(input1), _lib.ptr(input2), _lib.ptr(grad_output), _lib.ptr(g1), _lib.ptr(g2),
-            None, 0, B, C, H, W, kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
+            ws, ws_bytes, B, C, H, W, kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
             dilation_patchH, dilation_patchW, dH, dW, dt, _lib.current_stream(input1.device))
     _lib.check(code, "b200corr_sampler_backward")
     return [g1, g2]

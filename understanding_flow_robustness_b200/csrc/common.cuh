@@ -66,8 +66,10 @@ bool sampler_fast_applicable(int B, int C, int H, int W, const int *q, int dtype
 int sampler_fast_forward(const float *in1, const float *in2, float *out, int B, int C, int H, int W,
                          const int *q, cudaStream_t stream);
 int sampler_fast_backward(const float *in1, const float *in2, const float *gout, float *gin1,
-                          float *gin2, int B, int C, int H, int W, const int *q,
+                          float *gin2, int B, int C, int H, int W, const int *q, const int *plan,
                           cudaStream_t stream);
+size_t sampler_fast_backward_plan_ints(int B, int C, int H, int W, const int *q);
+int sampler_fast_backward_plan(int B, int C, int H, int W, const int *q, int *h_plan, size_t bytes);
 
 }  // namespace b200
 

@@ -40,9 +40,25 @@ size_t b200corr_sampler_forward_workspace_bytes(int, int, int, int, int, int, in
                                                 int, int, int, int, int, int, int) {
   return 0;
 }
-size_t b200corr_sampler_backward_workspace_bytes(int, int, int, int, int, int, int, int, int, int,
-                                                 int, int, int, int, int, int, int) {
-  return 0;
+size_t b200corr_sampler_backward_workspace_bytes(int B, int C, int H, int W, int kH, int kW,
+                                                 int patchH, int patchW, int padH, int padW,
+                                                 int dilationH, int dilationW, int dilation_patchH,
+                                                 int dilation_patchW, int dH, int dW, int dtype) {
+  const int q[12] = {kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
+                     dilation_patchH, dilation_patchW, dH, dW};
+  if (!b200::sampler_fast_applicable(B, C, H, W, q, dtype, 1)) return 0;
+  return sizeof(int) * b200::sampler_fast_backward_plan_ints(B, C, H, W, q);
+}
+
+int b200corr_sampler_backward_plan(int B, int C, int H, int W, int kH, int kW, int patchH,
+                                   int patchW, int padH, int padW, int dilationH, int dilationW,
+                                   int dilation_patchH, int dilation_patchW, int dH, int dW,
+                                   int dtype, void *h_plan, size_t bytes) {
+  const int q[12] = {kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
+                     dilation_patchH, dilation_patchW, dH, dW};
+  if (!b200::sampler_fast_applicable(B, C, H, W, q, dtype, 1)) return 0;
+  B200_CHECK(h_plan, "sampler_backward_plan: null buffer");
+  return b200::sampler_fast_backward_plan(B, C, H, W, q, (int *)h_plan, bytes);
 }
 
 int b200corr_sampler_uses_fast_path(int B, int C, int H, int W, int kH, int kW, int patchH,
@@ -80,8 +96,6 @@ int b200corr_sampler_backward(const void *in1, const void *in2, const void *grad
                               int patchH, int patchW, int padH, int padW, int dilationH,
                               int dilationW, int dilation_patchH, int dilation_patchW, int dH,
                               int dW, int dtype, void *stream_) {
-  (void)workspace;
-  (void)workspace_bytes;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int q[12] = {kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
                      dilation_patchH, dilation_patchW, dH, dW};
@@ -90,10 +104,14 @@ int b200corr_sampler_backward(const void *in1, const void *in2, const void *grad
   if ((size_t)B * C * H * W == 0) return 0;
   B200_CHECK(in1 && in2 && grad_in1 && grad_in2, "sampler_backward: null pointer");
   B200_CHECK(grad_out || (size_t)patchH * patchW * oH * oW == 0, "sampler_backward: null grad_out");
-  if (b200::sampler_fast_applicable(B, C, H, W, q, dtype, 1))
+  if (b200::sampler_fast_applicable(B, C, H, W, q, dtype, 1)) {
+    // workspace (optional): the device copy of b200corr_sampler_backward_plan()'s schedule
+    const size_t need = sizeof(int) * b200::sampler_fast_backward_plan_ints(B, C, H, W, q);
+    const int *plan = (workspace && need > 0 && workspace_bytes >= need) ? (const int *)workspace : nullptr;
     return b200::sampler_fast_backward((const float *)in1, (const float *)in2,
                                        (const float *)grad_out, (float *)grad_in1,
-                                       (float *)grad_in2, B, C, H, W, q, stream);
+                                       (float *)grad_in2, B, C, H, W, q, plan, stream);
+  }
   return b200::sampler_generic_backward(in1, in2, grad_out, grad_in1, grad_in2, B, C, H, W, oH, oW,
                                         q, dtype, stream);
 }

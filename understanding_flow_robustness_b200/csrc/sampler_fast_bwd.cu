@@ -18,6 +18,10 @@
 // same `other` address (multicast), the 8 channel-lanes read the same grad_output address.
 // Source rows outside the image are never visited, so work tracks the in-bounds MAC count.
 // Persistent CTAs, one per SM, a TMA/mbarrier ring over source rows that runs across units.
+#include <algorithm>
+#include <queue>
+#include <vector>
+
 #include "sampler_fast.cuh"
 
 namespace {
@@ -57,6 +61,7 @@ struct BwdCfg {
 };
 
 struct BwdParams {
+  const int *plan;   // optional LPT schedule: [grid+1] offsets then unit ids (device memory), or nullptr
   int B, C, H, W, dpH, NCT, NCB, total_units;
   b200::SamplerGroups g;   // prefix[] unused here (every group has NCT*NCB units)
 };
@@ -180,12 +185,18 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
   }
   __syncthreads();
 
-  const int nunits = p.total_units;
+  // unit sequence of this CTA: the host's LPT plan if given, else static round-robin
+  const int *plan = p.plan;
+  const int it_end = plan ? plan[blockIdx.x + 1] : p.total_units;
+  const int it_step = plan ? 1 : (int)gridDim.x;
+  const int it_begin = plan ? plan[blockIdx.x] : (int)blockIdx.x;
+  const int *ulist = plan ? plan + gridDim.x + 1 : nullptr;
+  const int nunits = it_end;
 
   // ---- producer (thread 0): walks (unit, source row) NST-1 steps ahead of the math
-  int pu = blockIdx.x, ps = 0;
+  int pu = it_begin, ps = 0;
   uint32_t pq = 0;
-  if (tid == 0 && pu < nunits) decode_bunit<Cfg>(p, pu, px);
+  if (tid == 0 && pu < nunits) decode_bunit<Cfg>(p, ulist ? ulist[pu] : pu, px);
   auto issue = [&]() {
     if (pu >= nunits) return;
     const int st = pq % NST;
@@ -218,17 +229,17 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
     ++pq;
     if (++ps == px.nsteps) {
       ps = 0;
-      pu += gridDim.x;
-      if (pu < nunits) decode_bunit<Cfg>(p, pu, px);
+      pu += it_step;
+      if (pu < nunits) decode_bunit<Cfg>(p, ulist ? ulist[pu] : pu, px);
     }
   };
   if (tid == 0)
     for (int s = 0; s < NST - 1; ++s) issue();
 
   uint32_t q = 0;
-  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+  for (int ui = it_begin; ui < nunits; ui += it_step) {
     BUnit x;
-    decode_bunit<Cfg>(p, u, x);
+    decode_bunit<Cfg>(p, ulist ? ulist[ui] : ui, x);
     const int s = x.s0 + li;
     // per-thread offsets inside a stage
     const int offv = (cset * 64 + lj) * NC + cgw * T;
@@ -279,10 +290,11 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
   }
 }
 
+// fills the group table / unit counts shared by the launcher and the planner
+// fills the group table / unit counts shared by the launcher and the planner
 template <class Cfg>
-int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, int H, int W,
-               int dpH, cudaStream_t stream) {
-  BwdParams p;
+int bwd_geometry(BwdParams &p, int B, int C, int H, int W, int dpH) {
+  p.plan = nullptr;
   p.B = B; p.C = C; p.H = H; p.W = W; p.dpH = dpH;
   p.NCT = (W + Cfg::COLS - 1) / Cfg::COLS;
   p.NCB = C / Cfg::CH_UNIT;
@@ -300,6 +312,64 @@ int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, 
   p.g.ngroups = ng;
   p.g.units_per_sample = ng * p.NCT * p.NCB;
   p.total_units = p.g.units_per_sample * B;
+  return 0;
+}
+
+// source rows one unit of group gi walks (its cost)
+template <class Cfg>
+int bwd_group_steps(const BwdParams &p, int gi) {
+  const int NS = b200::sublattice_rows(p.H, p.dpH, p.g.rp[gi]);
+  const int s0 = p.g.s0[gi];
+  const int s_last = s0 + 3 < NS - 1 ? s0 + 3 : NS - 1;
+  const int Rlo = s0 - Cfg::RH > 0 ? s0 - Cfg::RH : 0;
+  const int Rhi = s_last + Cfg::RH < NS - 1 ? s_last + Cfg::RH : NS - 1;
+  return Rhi - Rlo + 1;
+}
+
+static inline int bwd_grid(int total_units) {
+  return total_units < b200::num_sms() ? total_units : b200::num_sms();
+}
+
+// Longest-processing-time-first schedule of the units over `grid` persistent CTAs.
+// h_plan: [grid + 1] offsets, then total_units unit ids.  Host only.
+template <class Cfg>
+int bwd_plan(int B, int C, int H, int W, int dpH, int grid, int *h_plan, size_t bytes) {
+  BwdParams p;
+  if (int e = bwd_geometry<Cfg>(p, B, C, H, W, dpH)) return e;
+  B200_CHECK(bytes >= sizeof(int) * ((size_t)grid + 1 + p.total_units), "sampler_backward_plan: buffer too small");
+  const int per_group = p.NCT * p.NCB;
+  std::vector<int> cost(p.g.ngroups);
+  for (int gi = 0; gi < p.g.ngroups; ++gi) cost[gi] = bwd_group_steps<Cfg>(p, gi);
+  std::vector<int> units(p.total_units);
+  for (int u = 0; u < p.total_units; ++u) units[u] = u;
+  auto cost_of = [&](int u) { return cost[(u % p.g.units_per_sample) / per_group]; };
+  std::stable_sort(units.begin(), units.end(), [&](int a, int b) { return cost_of(a) > cost_of(b); });
+  using Bin = std::pair<long long, int>;  // (load, cta)
+  std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> heap;
+  for (int c = 0; c < grid; ++c) heap.push({0, c});
+  std::vector<std::vector<int>> lists(grid);
+  for (int u : units) {
+    Bin b = heap.top();
+    heap.pop();
+    lists[b.second].push_back(u);
+    heap.push({b.first + cost_of(u), b.second});
+  }
+  int off = 0;
+  int *ids = h_plan + grid + 1;
+  for (int c = 0; c < grid; ++c) {
+    h_plan[c] = off;
+    for (int u : lists[c]) ids[off++] = u;
+  }
+  h_plan[grid] = off;
+  return 0;
+}
+
+template <class Cfg>
+int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, int H, int W,
+               int dpH, const int *plan, cudaStream_t stream) {
+  BwdParams p;
+  if (int e = bwd_geometry<Cfg>(p, B, C, H, W, dpH)) return e;
+  p.plan = plan;
   if (p.total_units == 0) return 0;
 
   CUtensorMap map_o, map_g;
@@ -329,7 +399,7 @@ int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, 
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  const int grid = p.total_units < b200::num_sms() ? p.total_units : b200::num_sms();
+  const int grid = bwd_grid(p.total_units);
   kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(map_o, map_g, gin, p);
   B200_LAUNCH_OK(Cfg::WHICH == 1 ? "sampler_bwd_kernel<gIn1>" : "sampler_bwd_kernel<gIn2>");
   return 0;
@@ -340,20 +410,42 @@ int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, 
 namespace b200 {
 
 int sampler_fast_backward(const float *in1, const float *in2, const float *gout, float *gin1,
-                          float *gin2, int B, int C, int H, int W, const int *q,
+                          float *gin2, int B, int C, int H, int W, const int *q, const int *plan,
                           cudaStream_t stream) {
   const int patchH = q[2], patchW = q[3], dpH = q[8], dpW = q[9];
   if (patchH == 21 && patchW == 21 && dpW == 2) {
-    if (int e = launch_bwd<BwdCfg<21, 21, 2, 1>>(in2, gout, gin1, B, C, H, W, dpH, stream)) return e;
-    return launch_bwd<BwdCfg<21, 21, 2, 2>>(in1, gout, gin2, B, C, H, W, dpH, stream);
+    if (int e = launch_bwd<BwdCfg<21, 21, 2, 1>>(in2, gout, gin1, B, C, H, W, dpH, plan, stream)) return e;
+    return launch_bwd<BwdCfg<21, 21, 2, 2>>(in1, gout, gin2, B, C, H, W, dpH, plan, stream);
   }
   if (patchH == 9 && patchW == 9 && dpW == 1) {
-    if (int e = launch_bwd<BwdCfg<9, 9, 1, 1>>(in2, gout, gin1, B, C, H, W, dpH, stream)) return e;
-    return launch_bwd<BwdCfg<9, 9, 1, 2>>(in1, gout, gin2, B, C, H, W, dpH, stream);
+    if (int e = launch_bwd<BwdCfg<9, 9, 1, 1>>(in2, gout, gin1, B, C, H, W, dpH, plan, stream)) return e;
+    return launch_bwd<BwdCfg<9, 9, 1, 2>>(in1, gout, gin2, B, C, H, W, dpH, plan, stream);
   }
   set_error("sampler_fast_backward: no instantiation for patch %dx%d dilation_patch_w %d", patchH,
             patchW, dpW);
   return -1;
+}
+
+// number of ints of the backward plan (0 if the problem has no units)
+size_t sampler_fast_backward_plan_ints(int B, int C, int H, int W, const int *q) {
+  BwdParams p;
+  const int patchH = q[2];
+  int e = patchH == 21 ? bwd_geometry<BwdCfg<21, 21, 2, 1>>(p, B, C, H, W, q[8])
+                       : bwd_geometry<BwdCfg<9, 9, 1, 1>>(p, B, C, H, W, q[8]);
+  if (e || p.total_units == 0) return 0;
+  return (size_t)bwd_grid(p.total_units) + 1 + p.total_units;
+}
+
+int sampler_fast_backward_plan(int B, int C, int H, int W, const int *q, int *h_plan, size_t bytes) {
+  const size_t n = sampler_fast_backward_plan_ints(B, C, H, W, q);
+  if (n == 0) return 0;
+  BwdParams p;
+  if (q[2] == 21) {
+    bwd_geometry<BwdCfg<21, 21, 2, 1>>(p, B, C, H, W, q[8]);
+    return bwd_plan<BwdCfg<21, 21, 2, 1>>(B, C, H, W, q[8], bwd_grid(p.total_units), h_plan, bytes);
+  }
+  bwd_geometry<BwdCfg<9, 9, 1, 1>>(p, B, C, H, W, q[8]);
+  return bwd_plan<BwdCfg<9, 9, 1, 1>>(B, C, H, W, q[8], bwd_grid(p.total_units), h_plan, bytes);
 }
 
 // The structure the register-blocked kernels cover (everything else runs on sampler_generic.cu).
