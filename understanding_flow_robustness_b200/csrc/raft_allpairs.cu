@@ -15,7 +15,8 @@
 //                   TMEM, double buffered (2 x 256 columns) so the epilogue of tile i overlaps the
 //                   MMAs of tile i+1
 //        warp 2   : TMEM allocator
-//        warps 4-7: epilogue.  Each thread owns one query row = a full 8x32 patch of keys, so the
+//        warps 4-11: epilogue (two warps per TMEM lane quarter, 4 patch rows each).  A query row's
+//                   8x32 patch of keys lives in the registers of two threads, so the
 //                   2x2, 4x4 and 8x8 average pools are register-local.  Level 0 goes
 //                   TMEM -> regs -> swizzled smem -> TMA store (whole 128-byte lines); levels 1-3 are
 //                   written straight from registers (64/32/16-byte runs).
@@ -25,6 +26,8 @@
 // Error bound of the TF32 path (documented in DESIGN.md, asserted in tests): inputs are rounded to
 // 11 significant bits (rel. error <= 2^-11 each), products accumulate in fp32, so
 //     |vol - exact| <= (2^-10 + 2^-22) * scale * sum_c |f1_c * f2_c|  (+ fp32 accumulation error).
+#include <cstdlib>
+
 #include "tcgen05.cuh"
 
 namespace {
@@ -60,14 +63,18 @@ constexpr int PH = 8, PW = 32;  // key patch
 constexpr int NST = 3;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_ROW_BYTES = 32 * 128;                 // one TMA store box: 32 query rows x 32 floats
-constexpr int EPI_WARP_BYTES = 2 * 2 * EPI_ROW_BYTES;   // [double buffer][2 patch rows]
-constexpr int SMEM_BYTES = NST * STAGE_BYTES + 4 * EPI_WARP_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_WARP_BYTES = 2 * EPI_ROW_BYTES;       // double-buffered staging of one patch row
+constexpr int EPI_WARPS = 8;
+constexpr int XBUF_BYTES = 2 * 4 * 32 * 16;               // level-3 exchange between the two halves
+constexpr int SMEM_BYTES = NST * STAGE_BYTES + EPI_WARPS * EPI_WARP_BYTES + XBUF_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int THREADS = 384;
 constexpr int TMEM_COLS = 512;
 
 struct Params {
   int B, HW, H, W, KB;       // KB = Cp / 32
   int MT, NTY, NTX;          // tile counts
   float scale;
+  int debug;                 // B200CORR_DEBUG bits (diagnostics): 1 skip level-0 stores, 2 skip pooled stores
   float *lvl[3];             // levels 1..3 (nullptr if not requested)
   int LH[3], LW[3];
 };
@@ -88,7 +95,7 @@ __device__ __forceinline__ void store_row_vec(float *dst, const float (&v)[N], i
   }
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(tc::THREADS, 1)
 allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const __grid_constant__ CUtensorMap mapC, const tc::Params p) {
   using namespace tc;
@@ -98,7 +105,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *sm = smem_raw + (base - raw);
   uint8_t *epi = sm + NST * STAGE_BYTES;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(epi + 4 * EPI_WARP_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(epi + EPI_WARPS * EPI_WARP_BYTES + XBUF_BYTES);
   uint64_t *full_bar = bars, *empty_bar = bars + NST;
   uint64_t *tfull_bar = bars + 2 * NST, *tempty_bar = bars + 2 * NST + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 4);
@@ -115,7 +122,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -174,9 +181,12 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue (warp w may only touch TMEM lanes 32*(w%4) .. +31)
-    const int wq = warp & 3;
-    uint8_t *ebuf = epi + wq * EPI_WARP_BYTES;
+    // ================= epilogue: 8 warps.  Warp w may only touch TMEM lanes 32*(w%4) .. +31; the two
+    // warps of a lane quarter split the patch rows (columns): half 0 -> rows 0-3, half 1 -> rows 4-7.
+    const int wq = warp & 3, half = (warp - 4) >> 2;
+    uint8_t *ebuf = epi + (warp - 4) * EPI_WARP_BYTES;
+    float4 *xbuf = reinterpret_cast<float4 *>(epi + 8 * EPI_WARP_BYTES);  // [2][4][32] level-3 exchange
+    const bool m_dbg = !(p.debug & 2);
     const bool v1 = p.lvl[0] && (p.LW[0] % 4 == 0), v2 = p.lvl[1] && (p.LW[1] % 4 == 0),
                v3 = p.lvl[2] && (p.LW[2] % 4 == 0);
     uint32_t lt = 0, sbuf = 0;
@@ -185,88 +195,90 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       const int y0 = (nt / p.NTX) * PH, x0 = (nt % p.NTX) * PW;
       const int mrow0 = mt * BM + wq * 32;
       const int m = mrow0 + lane;
-      const bool m_ok = m < p.HW;
+      const bool m_ok = m < p.HW && m_dbg;
       const size_t q = (size_t)b * p.HW + (m_ok ? m : 0);
       const int buf = lt & 1;
       mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(wq * 32) << 16);
+      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(wq * 32) << 16) + half * 128;
 
-      float p1prev[16], p2prev[8];
+      float prev[32], p1prev[16], p2[8];
 #pragma unroll
       for (int step = 0; step < 4; ++step, sbuf ^= 1) {
-        float r0[32], r1[32];
-        tmem_ld_32x32(taddr + step * 64, r0);
-        tmem_ld_32x32(taddr + step * 64 + 32, r1);
-        // the staging buffer written two steps ago must have been read by its TMA stores
+        const int r = half * 4 + step;  // patch row
+        float cur[32];
+        tmem_ld_32x32(taddr + step * 32, cur);
+        // the staging buffer written two steps ago must have been read by its TMA store
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          r0[i] *= p.scale;
-          r1[i] *= p.scale;
-        }
-        // ---- level 0: two patch rows -> swizzled staging -> TMA store
-        uint8_t *s0 = ebuf + sbuf * (2 * EPI_ROW_BYTES);
-        uint8_t *s1 = s0 + EPI_ROW_BYTES;
+        for (int i = 0; i < 32; ++i) cur[i] *= p.scale;
+        // ---- level 0: one patch row -> swizzled staging -> TMA store (32 query rows x 128 B)
+        uint8_t *s0 = ebuf + sbuf * EPI_ROW_BYTES;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int off = lane * 128 + ((j ^ (lane & 7)) << 4);
-          *reinterpret_cast<float4 *>(s0 + off) = make_float4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
-          *reinterpret_cast<float4 *>(s1 + off) = make_float4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
+          *reinterpret_cast<float4 *>(s0 + off) = make_float4(cur[4 * j], cur[4 * j + 1], cur[4 * j + 2], cur[4 * j + 3]);
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          tma_store_4d(&mapC, s0, x0, y0 + 2 * step, mrow0, b);
-          tma_store_4d(&mapC, s1, x0, y0 + 2 * step + 1, mrow0, b);
+        if (lane == 0 && !(p.debug & 1)) {
+          tma_store_4d(&mapC, s0, x0, y0 + r, mrow0, b);
           tma_store_commit();
         }
-        // ---- level 1: 2x2 means of the two rows -> 16 values
-        float p1[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          p1[j] = (((r0[2 * j] + r0[2 * j + 1]) + r1[2 * j]) + r1[2 * j + 1]) * 0.25f;
-        if (p.lvl[0] && m_ok) {
-          const int y1 = y0 / 2 + step, x1 = x0 / 2;
-          if (y1 < p.LH[0])
-            store_row_vec(p.lvl[0] + (q * p.LH[0] + y1) * p.LW[0] + x1, p1, x1, p.LW[0], v1);
-        }
         if (step & 1) {
-          // ---- level 2: means of two level-1 rows -> 8 values
-          float p2[8];
+          // ---- level 1: 2x2 means of rows (r-1, r) -> 16 values
+          float p1[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            p2[j] = (((p1prev[2 * j] + p1prev[2 * j + 1]) + p1[2 * j]) + p1[2 * j + 1]) * 0.25f;
-          if (p.lvl[1] && m_ok) {
-            const int y2 = y0 / 4 + (step >> 1), x2 = x0 / 4;
-            if (y2 < p.LH[1])
-              store_row_vec(p.lvl[1] + (q * p.LH[1] + y2) * p.LW[1] + x2, p2, x2, p.LW[1], v2);
+          for (int j = 0; j < 16; ++j)
+            p1[j] = (((prev[2 * j] + prev[2 * j + 1]) + cur[2 * j]) + cur[2 * j + 1]) * 0.25f;
+          if (p.lvl[0] && m_ok) {
+            const int y1 = y0 / 2 + (r >> 1), x1 = x0 / 2;
+            if (y1 < p.LH[0])
+              store_row_vec(p.lvl[0] + (q * p.LH[0] + y1) * p.LW[0] + x1, p1, x1, p.LW[0], v1);
           }
           if (step == 3) {
-            float p3[4];
+            // ---- level 2: means of the two level-1 rows of this half -> 8 values
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              p3[j] = (((p2prev[2 * j] + p2prev[2 * j + 1]) + p2[2 * j]) + p2[2 * j + 1]) * 0.25f;
-            if (p.lvl[2] && m_ok) {
-              const int y3 = y0 / 8, x3 = x0 / 8;
-              if (y3 < p.LH[2])
-                store_row_vec(p.lvl[2] + (q * p.LH[2] + y3) * p.LW[2] + x3, p3, x3, p.LW[2], v3);
+            for (int j = 0; j < 8; ++j)
+              p2[j] = (((p1prev[2 * j] + p1prev[2 * j + 1]) + p1[2 * j]) + p1[2 * j + 1]) * 0.25f;
+            if (p.lvl[1] && m_ok) {
+              const int y2 = y0 / 4 + half, x2 = x0 / 4;
+              if (y2 < p.LH[1])
+                store_row_vec(p.lvl[1] + (q * p.LH[1] + y2) * p.LW[1] + x2, p2, x2, p.LW[1], v2);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) p2prev[j] = p2[j];
+            for (int j = 0; j < 16; ++j) p1prev[j] = p1[j];
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) p1prev[j] = p1[j];
+          for (int i = 0; i < 32; ++i) prev[i] = cur[i];
         }
       }
       // all TMEM reads of this accumulator buffer are done: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      // ---- level 3: the 8x8 mean needs the level-2 rows of both halves -> exchange through smem
+      float4 *xs = xbuf + ((lt & 1) * 4 + wq) * 32 + lane;
+      if (half == 0)
+        *xs = make_float4(p2[0] + p2[1], p2[2] + p2[3], p2[4] + p2[5], p2[6] + p2[7]);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
+      if (half == 1) {
+        const float4 h = *xs;
+        float p3[4];
+        p3[0] = ((h.x + p2[0]) + p2[1]) * 0.25f;
+        p3[1] = ((h.y + p2[2]) + p2[3]) * 0.25f;
+        p3[2] = ((h.z + p2[4]) + p2[5]) * 0.25f;
+        p3[3] = ((h.w + p2[6]) + p2[7]) * 0.25f;
+        if (p.lvl[2] && m_ok) {
+          const int y3 = y0 / 8, x3 = x0 / 8;
+          if (y3 < p.LH[2])
+            store_row_vec(p.lvl[2] + (q * p.LH[2] + y3) * p.LW[2] + x3, p3, x3, p.LW[2], v3);
+        }
+      }
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
@@ -426,6 +438,10 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
     p.NTY = (H + tc::PH - 1) / tc::PH;
     p.NTX = (W + tc::PW - 1) / tc::PW;
     p.scale = scale;
+    {
+      const char *dbg = getenv("B200CORR_DEBUG");
+      p.debug = dbg ? atoi(dbg) : 0;
+    }
     for (int l = 0; l < 3; ++l) {
       const bool want = l + 1 < num_levels && LH[l + 1] * LW[l + 1] > 0;
       p.lvl[l] = want ? h_levels[l + 1] : nullptr;
@@ -442,7 +458,7 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
     }
     const int total = B * p.MT * p.NTY * p.NTX;
     const int grid = total < b200::num_sms() ? total : b200::num_sms();
-    allpairs_tc_kernel<<<grid, 256, tc::SMEM_BYTES, stream>>>(mapA, mapB, mapC, p);
+    allpairs_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(mapA, mapB, mapC, p);
     B200_LAUNCH_OK("allpairs_tc_kernel");
   }
   for (int l = first_unpooled; l < num_levels; ++l)

@@ -71,8 +71,12 @@ template <int R>
 __device__ __forceinline__ void build_taps(TapTables<R> &tt, const float *coords, int b, int q0,
                                            int HW, int lvl, int LH, int LW, int mode) {
   constexpr int N = Geo<R>::N;
-  for (int i = threadIdx.x; i < QT * 2; i += blockDim.x) {
-    const int qi = i >> 1, axis = i & 1;
+  // one task per (query, axis, tap): 32 * 2 * N tasks spread over the whole CTA (the two IEEE
+  // divisions of the grid_sample round trip make a tap ~80 instructions)
+  for (int i = threadIdx.x; i < QT * 2 * N; i += blockDim.x) {
+    const int t = i % N;
+    const int qa = i / N;
+    const int qi = qa >> 1, axis = qa & 1;
     const int q = q0 + qi;
     float c = 0.f;
     if (q < HW) c = coords[((size_t)b * 2 + axis) * HW + q];
@@ -82,23 +86,23 @@ __device__ __forceinline__ void build_taps(TapTables<R> &tt, const float *coords
     float fo = floorf(cl);
     if (!(fabsf(fo) < 1e8f)) fo = -1e8f;  // non-finite / absurd coordinates: everything out of range
     const int org = (int)fo - R - 1;
-    if (axis == 0) tt.ox[qi] = org; else tt.oy[qi] = org;
-    for (int t = 0; t < N; ++t) {
-      const float x = sample_coord(c, lvl, t - R, size, mode);
-      float fx = floorf(x);
-      int rel;
-      float frac;
-      if (fabsf(fx) < 1e8f) {
-        rel = (int)fx - org;
-        frac = x - fx;
-        // the round trip moves x by a few ulp at most: rel is within [0, WS-2]; clamp defensively
-        if (rel < 0 || rel > Geo<R>::WS - 2) { rel = 0; frac = 0.f; fx = -1e9f; }
-      } else {
-        rel = 0; frac = x - x;  // NaN propagates like in the reference
-      }
-      if (axis == 0) { tt.x0[qi][t] = (fx < -1e8f) ? -1 : rel; tt.ax[qi][t] = frac; }
-      else           { tt.y0[qi][t] = (fx < -1e8f) ? -1 : rel; tt.ay[qi][t] = frac; }
+    if (t == 0) {
+      if (axis == 0) tt.ox[qi] = org; else tt.oy[qi] = org;
     }
+    const float x = sample_coord(c, lvl, t - R, size, mode);
+    float fx = floorf(x);
+    int rel;
+    float frac;
+    if (fabsf(fx) < 1e8f) {
+      rel = (int)fx - org;
+      frac = x - fx;
+      // the round trip moves x by a few ulp at most: rel is within [0, WS-2]; clamp defensively
+      if (rel < 0 || rel > Geo<R>::WS - 2) { rel = -1; frac = 0.f; }
+    } else {
+      rel = 0; frac = x - x;  // NaN propagates like in the reference
+    }
+    if (axis == 0) { tt.x0[qi][t] = rel; tt.ax[qi][t] = frac; }
+    else           { tt.y0[qi][t] = rel; tt.ay[qi][t] = frac; }
   }
 }
 

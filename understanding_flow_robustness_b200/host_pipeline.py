@@ -1,0 +1,63 @@
+"""Host-buffer front end of the sampler: `correlate_host_batches`.
+
+The reference's operator takes device tensors; a caller that holds its feature maps in host memory
+pays H2D + kernel + D2H per batch.  This helper runs a stream of host batches through
+`spatial_correlation_sample` forward+backward with three CUDA streams (copy-in, compute, copy-out)
+and two device buffer sets, so the PCIe transfers of batch i+1 / i-1 overlap the kernels of batch i
+(PCIe is full duplex).  It is what bench.py's `e2e` measures.
+"""
+import torch
+
+from . import backend
+
+
+class SamplerHostPipeline:
+    def __init__(self, shape, hyper, device, depth=2):
+        B, C, H, W = shape
+        self.hyper = hyper
+        self.device = device
+        P1, P2 = hyper[2], hyper[3]
+        oH = backend.output_size(H, hyper[4], hyper[0], hyper[6], hyper[10])
+        oW = backend.output_size(W, hyper[5], hyper[1], hyper[7], hyper[11])
+        self.depth = depth
+        mk = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
+        self.dev_in = [(mk(B, C, H, W), mk(B, C, H, W), mk(B, P1, P2, oH, oW)) for _ in range(depth)]
+        self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(device) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]       # inputs of slot landed
+        self.ev_done = [torch.cuda.Event() for _ in range(depth)]     # kernels of slot finished
+        self.ev_free = [torch.cuda.Event() for _ in range(depth)]     # outputs of slot copied out
+        self.pending = [None] * depth
+        self.n = 0
+
+    def submit(self, h_in1, h_in2, h_gout, h_out, h_g1, h_g2):
+        """Enqueue one batch: pinned host inputs -> forward + backward -> pinned host outputs."""
+        k = self.n % self.depth
+        d1, d2, dg = self.dev_in[k]
+        with torch.cuda.stream(self.s_in):
+            if self.n >= self.depth:
+                self.s_in.wait_event(self.ev_done[k])     # previous kernels on this slot are done
+            d1.copy_(h_in1, non_blocking=True)
+            d2.copy_(h_in2, non_blocking=True)
+            dg.copy_(h_gout, non_blocking=True)
+            self.ev_in[k].record(self.s_in)
+        with torch.cuda.stream(self.s_compute):
+            self.s_compute.wait_event(self.ev_in[k])
+            if self.n >= self.depth:
+                self.s_compute.wait_event(self.ev_free[k])  # previous outputs of this slot were copied out
+            out = backend.forward(d1, d2, *self.hyper)
+            g1, g2 = backend.backward(d1, d2, dg, *self.hyper)
+            self.ev_done[k].record(self.s_compute)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_done[k])
+            h_out.copy_(out, non_blocking=True)
+            h_g1.copy_(g1, non_blocking=True)
+            h_g2.copy_(g2, non_blocking=True)
+            self.ev_free[k].record(self.s_out)
+        for t in (out, g1, g2):
+            t.record_stream(self.s_out)
+        self.pending[k] = (out, g1, g2)
+        self.n += 1
+
+    def synchronize(self):
+        for s in (self.s_in, self.s_compute, self.s_out):
+            s.synchronize()
