@@ -381,6 +381,20 @@ def attack_bench(dev, rank, world, global_batch):
     def it(pt):
         return attack.patch_attack_iteration(net, i1, i2, pt, mask, init, cfg, global_batch, g)[0]
 
+    # BASELINE config 2 on the way: whole-network forward+backward pairs/s of this rank's shard
+    def net_step():
+        a = i1[:8].clone().requires_grad_(True)
+        net(a, i2[:8]).mean().backward()
+    net_step()
+    torch.cuda.synchronize()
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record()
+    for _ in range(3):
+        net_step()
+    n1.record()
+    torch.cuda.synchronize()
+    net_pairs_per_s = min(8, len(idx)) * 3 / (n0.elapsed_time(n1) * 1e-3)
+
     patch = it(patch)                                      # warm-up (cuDNN autotune, allocator)
     if world > 1:
         dist.barrier()
@@ -404,7 +418,9 @@ def attack_bench(dev, rank, world, global_batch):
             "pairs_per_rank": len(idx), "n_gpus": world,
             "config": "FlowNetC harness (random init) 384x1280, 100x100 circular patch, max_count 2, cosine loss, "
                       "patch-gradient all-reduce (NCCL) per inner step",
-            "allreduce_bytes": int(patch.numel() * 4 + 4)}
+            "allreduce_bytes": int(patch.numel() * 4 + 4),
+            "flownetc_fwd_bwd_pairs_per_s_per_gpu": net_pairs_per_s,
+            "flownetc_config": "BASELINE config 2: FlowNetC harness random init, forward+backward, 384x1280, batch 8, 1 GPU"}
 
 
 def raft_bench(dev):
