@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200corr.so")
+LIB_PATH = os.environ.get("B200CORR_LIB") or os.path.join(_HERE, "libb200corr.so")   # env override: tuning variants
 
 _lib = None
 

@@ -14,7 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
-LIB = os.path.join(HERE, "libb200corr.so")
+SUFFIX = os.environ.get("B200_LIB_SUFFIX", "")          # tuning variants: separate objects + library
+OBJ = OBJ + SUFFIX
+LIB = os.path.join(HERE, f"libb200corr{SUFFIX}.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
@@ -23,7 +25,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-I", os.path.join(ROOT, "include"),
     "-I", CSRC,
-]
+] + os.environ.get("B200_EXTRA_NVCC", "").split()
 
 
 def _sources():

@@ -37,8 +37,8 @@ constexpr int round_up_c(int a, int b) { return (a + b - 1) / b * b; }
 template <int PH_, int PW_, int DPW_, int WHICH_>
 struct BwdCfg {
   static constexpr int PH = PH_, PW = PW_, DPW = DPW_, WHICH = WHICH_;
-  static constexpr int T = 8, NCH = 8, CSETS = 2, CGROUPS = 4;
-  static constexpr int CH_UNIT = 8 * NCH * CSETS;     // 128 channels per unit
+  static constexpr int T = 8, NCH = 8, CGROUPS = 4;
+  static constexpr int CH_UNIT = 16 * NCH;            // 128 channels per unit (16 channel lanes x NCH)
   static constexpr int COLS = CGROUPS * T;            // 32 pixels per unit row
   static constexpr int RH = (PH - 1) / 2, RW = (PW - 1) / 2;
   static constexpr int HALO = RW * DPW;
@@ -126,7 +126,7 @@ __device__ __forceinline__ void bwd_pass(float2 (&acc2)[Cfg::T / 2][Cfg::NCH], c
   for (int ci = 0; ci < Cfg::NCH; ++ci) {
 #pragma unroll
     for (int sg = 0; sg < NL; ++sg) {
-      const float4 v4 = lds128(vb + ci * 8 * NC + MB + 4 * sg);
+      const float4 v4 = lds128(vb + ci * 16 * NC + MB + 4 * sg);
       if constexpr (DPW % 2 == 0) {
         // pixel pair tp meets window pair tp + k'*DPW/2: one FFMA2 per (tp, k')
         const float2 vp[2] = {make_float2(v4.x, v4.y), make_float2(v4.z, v4.w)};
@@ -170,9 +170,14 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
   BUnit &px = *reinterpret_cast<BUnit *>(empty_bar + NST);  // producer-side unit (thread 0 only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // li fastest: the 4 row-lanes that read the same `other` address are adjacent (2-cycle LDS.128)
-  const int li = lane & 3, lj = lane >> 2;
-  const int cgw = warp & 3, cset = warp >> 2;
+  // Warp = 2 pixel rows (adjacent lanes: an aligned lane pair reads the same `other` address, the
+  // only sharing an LDS.128 merges) x 16 interleaved channel lanes x 8 channels each = 128 channels.
+  // The CTA's 8 warps are 4 column groups x 2 row pairs; a warp whose two rows are both outside the
+  // +-RH band of the current source row skips the step as a whole (22 of 24 steps useful instead of
+  // 84 of 96 lanes).
+  const int li = (lane & 1) + 2 * (warp >> 2);   // pixel row inside the group (0..3)
+  const int lj = lane >> 1;                      // channel lane (0..15)
+  const int cgw = warp & 3;
 
   if (tid == 0) {
     tma_prefetch_desc(&map_other);
@@ -242,7 +247,7 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
     decode_bunit<Cfg>(p, ulist ? ulist[ui] : ui, x);
     const int s = x.s0 + li;
     // per-thread offsets inside a stage
-    const int offv = (cset * 64 + lj) * NC + cgw * T;
+    const int offv = lj * NC + cgw * T;
     const int offg = Cfg::OTHER_FLOATS +
                      (Cfg::WHICH == 1 ? li * Cfg::GLI + cgw * T + 4 * li : li * PW * NC + cgw * T);
 
@@ -261,7 +266,8 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
       mbar_wait(&full_bar[st], (q / NST) & 1);
       const int R = x.Rlo + step;
       const int e = Cfg::WHICH == 1 ? R - s : s - R;
-      if (s < x.NS && e >= -RH && e <= RH) {
+      const bool live = s < x.NS && e >= -RH && e <= RH;
+      if (__any_sync(0xffffffffu, live) && live) {
         const float *vb = smem + st * Cfg::STAGE_FLOATS + offv;
         const float *gs = smem + st * Cfg::STAGE_FLOATS + offg;
         bwd_pass<Cfg, 0, Cfg::KA>(acc, gs, vb);
@@ -275,15 +281,15 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
       const int h = s * p.dpH + x.rp;
       const int x0 = x.c0 + cgw * T;
       const size_t HW = (size_t)p.H * p.W;
-      float *o = gin + ((size_t)x.n * p.C + x.cb * Cfg::CH_UNIT + cset * 64 + lj) * HW +
+      float *o = gin + ((size_t)x.n * p.C + x.cb * Cfg::CH_UNIT + lj) * HW +
                  (size_t)h * p.W + x0;
 #pragma unroll
       for (int ci = 0; ci < Cfg::NCH; ++ci) {
         if (x0 < p.W)
-          *reinterpret_cast<float4 *>(o + (size_t)ci * 8 * HW) =
+          *reinterpret_cast<float4 *>(o + (size_t)ci * 16 * HW) =
               make_float4(acc[0][ci].x, acc[0][ci].y, acc[1][ci].x, acc[1][ci].y);
         if (x0 + 4 < p.W)
-          *reinterpret_cast<float4 *>(o + (size_t)ci * 8 * HW + 4) =
+          *reinterpret_cast<float4 *>(o + (size_t)ci * 16 * HW + 4) =
               make_float4(acc[2][ci].x, acc[2][ci].y, acc[3][ci].x, acc[3][ci].y);
       }
     }

@@ -28,8 +28,21 @@
 //     3-stage mbarrier ring over 8-channel chunks that keeps running across unit boundaries.
 #include "sampler_fast.cuh"
 
+// tuning knobs (scripts/tune_sampler.py builds variants with -D...)
+#ifndef B200_FWD_CC
+#define B200_FWD_CC 8
+#endif
+#ifndef B200_FWD_NST
+#define B200_FWD_NST 3
+#endif
+#ifndef B200_FWD_UNROLL
+#define B200_FWD_UNROLL 2
+#endif
+
 namespace {
 using namespace b200dev;
+
+constexpr int kFwdUnroll = B200_FWD_UNROLL;
 
 constexpr int odd4(int x) {  // round up to a multiple of 4 floats whose 16-byte chunk count is odd
   int c = (x + 3) / 4;
@@ -49,8 +62,8 @@ struct FwdCfg {
   static constexpr int NRB = b200::kRowsPerGroup + PH - 1;  // in2 rows staged per unit
   static constexpr int NC1 = odd4(GMAX * T);
   static constexpr int NC2 = odd4(GMAX * T + (PW - 1) * DPW);
-  static constexpr int CC = 8;                         // channels per pipeline stage
-  static constexpr int NST = 3;                        // pipeline stages
+  static constexpr int CC = B200_FWD_CC;               // channels per pipeline stage
+  static constexpr int NST = B200_FWD_NST;             // pipeline stages
   static constexpr int IN2_FLOATS = CC * NRB * NC2;
   static constexpr int IN1_FLOATS = CC * b200::kRowsPerGroup * NC1;
   static constexpr int STAGE_FLOATS = IN2_FLOATS + IN1_FLOATS;
@@ -197,7 +210,7 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
       mbar_wait(&full_bar[st], (q / NST) & 1);
       const float *sb = smem + st * Cfg::STAGE_FLOATS + off2;
       const float *sa = smem + st * Cfg::STAGE_FLOATS + off1;
-#pragma unroll 2
+#pragma unroll kFwdUnroll
       for (int cc = 0; cc < CC; ++cc) {
         const float4 a0 = lds128(sa + cc * b200::kRowsPerGroup * NC1);
         const float4 a1 = lds128(sa + cc * b200::kRowsPerGroup * NC1 + 4);
