@@ -55,6 +55,12 @@ struct Geo {
   static constexpr int N = 2 * R + 1;      // taps per axis
   static constexpr int WS = 2 * R + 4;     // staged window per axis
   static constexpr int WSTRIDE = WS * WS + 1;
+  // vector path (level width % 4 == 0): a window row is fetched as NV4 aligned float4 covering
+  // [ox & ~3, ...) and stored shifted by (ox & 3); odd row / query pitches keep both the staging
+  // stores (lane = window row) and the sampling loads (lane = query) bank-conflict free
+  static constexpr int NV4 = (WS + 3 + 3) / 4;
+  static constexpr int VROW = WS | 1;
+  static constexpr int VSTRIDE = (WS * VROW) | 1;
 };
 
 // per-query per-axis tap tables in shared memory
@@ -106,11 +112,13 @@ __device__ __forceinline__ void build_taps(TapTables<R> &tt, const float *coords
   }
 }
 
-template <int R>
+template <int R, bool VEC>
 __global__ void __launch_bounds__(256)
 lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float *__restrict__ out) {
-  constexpr int N = Geo<R>::N, WS = Geo<R>::WS, WSTRIDE = Geo<R>::WSTRIDE;
-  __shared__ float win[QT * WSTRIDE];
+  constexpr int N = Geo<R>::N, WS = Geo<R>::WS;
+  constexpr int ROW = VEC ? Geo<R>::VROW : WS;
+  constexpr int QSTRIDE = VEC ? Geo<R>::VSTRIDE : Geo<R>::WSTRIDE;
+  __shared__ float win[QT * QSTRIDE];
   __shared__ TapTables<R> tt;
   const int lvl = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * QT;
   const int LH = p.LH[lvl], LW = p.LW[lvl];
@@ -123,42 +131,100 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
   for (int i = threadIdx.x; i < QT * WS; i += blockDim.x) {
     const int qi = i / WS, r = i - qi * WS;
     const int q = q0 + qi;
-    float *dst = win + qi * WSTRIDE + r * WS;
     const int y = tt.oy[qi] + r, xo = tt.ox[qi];
-    if (q < p.HW && y >= 0 && y < LH) {
-      const float *src = vol + (((size_t)b * p.HW + q) * LH + y) * LW;
+    const bool row_ok = q < p.HW && y >= 0 && y < LH;
+    if (VEC) {
+      float *dst = win + qi * QSTRIDE + r * ROW;
+      const int a0 = xo & ~3;  // aligned first column (floor to a multiple of 4, also for negatives)
+      const float4 *src = reinterpret_cast<const float4 *>(
+          vol + (((size_t)b * p.HW + (row_ok ? q : 0)) * LH + (row_ok ? y : 0)) * LW);
+      float v[Geo<R>::NV4 * 4];
 #pragma unroll
-      for (int c = 0; c < WS; ++c) {
-        const int x = xo + c;
-        dst[c] = (x >= 0 && x < LW) ? src[x] : 0.f;
+      for (int k = 0; k < Geo<R>::NV4; ++k) {
+        const int x = a0 + 4 * k;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok && x >= 0 && x < LW) val = __ldg(src + (x >> 2));
+        v[4 * k] = val.x; v[4 * k + 1] = val.y; v[4 * k + 2] = val.z; v[4 * k + 3] = val.w;
+      }
+      switch (xo & 3) {  // compile-time register indices inside each case
+        case 0:
+#pragma unroll
+          for (int c = 0; c < WS; ++c) dst[c] = v[c];
+          break;
+        case 1:
+#pragma unroll
+          for (int c = 0; c < WS; ++c) dst[c] = v[c + 1];
+          break;
+        case 2:
+#pragma unroll
+          for (int c = 0; c < WS; ++c) dst[c] = v[c + 2];
+          break;
+        default:
+#pragma unroll
+          for (int c = 0; c < WS; ++c) dst[c] = v[c + 3];
+          break;
       }
     } else {
+      float *dst = win + qi * QSTRIDE + r * ROW;
+      if (row_ok) {
+        const float *src = vol + (((size_t)b * p.HW + q) * LH + y) * LW;
 #pragma unroll
-      for (int c = 0; c < WS; ++c) dst[c] = 0.f;
+        for (int c = 0; c < WS; ++c) {
+          const int x = xo + c;
+          dst[c] = (x >= 0 && x < LW) ? src[x] : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < WS; ++c) dst[c] = 0.f;
+      }
     }
   }
   __syncthreads();
 
-  // phase 2: warp = taps, lane = query
+  // phase 2: lane = query, warp = y-offset row j; the x tap tables of the query live in registers
+  // and the two window rows are walked left to right, reusing the previous column pair whenever the
+  // next tap starts one pixel further (always, up to the reference's coordinate round-trip noise)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = q0 + lane;
-  const float *w = win + lane * WSTRIDE;
+  const float *w = win + lane * QSTRIDE;
   const int nchan = p.num_levels * N * N;
-  for (int k = warp; k < N * N; k += 8) {
-    const int i = k / N, j = k - i * N;  // i: x offset index, j: y offset index
-    const int rx = tt.x0[lane][i], ry = tt.y0[lane][j];
-    const float ax = tt.ax[lane][i], ay = tt.ay[lane][j];
-    float v = 0.f;
-    if (rx >= 0 && ry >= 0) {
-      const float *c = w + ry * WS + rx;
-      // grid_sample: nw = (x1-x)(y1-y), ne = (x-x0)(y1-y), sw = (x1-x)(y-y0), se = (x-x0)(y-y0)
-      const float bx = 1.f - ax, by = 1.f - ay;
-      v = c[0] * (bx * by);
-      v += c[1] * (ax * by);
-      v += c[WS] * (bx * ay);
-      v += c[WS + 1] * (ax * ay);
+  int rxs[N];
+  float axs[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    rxs[i] = tt.x0[lane][i];
+    axs[i] = tt.ax[lane][i];
+  }
+  for (int j = warp; j < N; j += 8) {
+    const int ry = tt.y0[lane][j];
+    const float ay = tt.ay[lane][j], by = 1.f - ay;
+    const float *r0 = w + (ry >= 0 ? ry : 0) * ROW;
+    int prx = -100;
+    float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int rx = rxs[i];
+      float v = 0.f;
+      if (rx >= 0 && ry >= 0) {
+        if (rx == prx + 1) {
+          c00 = c01;
+          c10 = c11;
+        } else {
+          c00 = r0[rx];
+          c10 = r0[ROW + rx];
+        }
+        c01 = r0[rx + 1];
+        c11 = r0[ROW + rx + 1];
+        prx = rx;
+        // grid_sample: nw = (x1-x)(y1-y), ne = (x-x0)(y1-y), sw = (x1-x)(y-y0), se = (x-x0)(y-y0)
+        const float ax = axs[i], bx = 1.f - ax;
+        v = c00 * (bx * by);
+        v += c01 * (ax * by);
+        v += c10 * (bx * ay);
+        v += c11 * (ax * ay);
+      }
+      if (q < p.HW) out[((size_t)b * nchan + lvl * N * N + i * N + j) * p.HW + q] = v;
     }
-    if (q < p.HW) out[((size_t)b * nchan + lvl * N * N + k) * p.HW + q] = v;
   }
 }
 
@@ -263,12 +329,18 @@ int b200corr_lookup_forward(const float *const *h_levels, int num_levels, const 
   if (B == 0) return 0;
   B200_CHECK(coords && out, "lookup_forward: null pointer");
   dim3 grid((p.HW + QT - 1) / QT, num_levels, B);
+  bool vec = true;  // aligned float4 staging needs every level width % 4 == 0 and 16-byte aligned bases
+  for (int l = 0; l < num_levels; ++l) vec = vec && p.LW[l] % 4 == 0 && ((uintptr_t)p.lvl[l] & 15) == 0;
+#define LOOKUP_FWD(RR)                                                              \
+  if (vec) lookup_fwd_kernel<RR, true><<<grid, 256, 0, stream>>>(p, coords, out);   \
+  else lookup_fwd_kernel<RR, false><<<grid, 256, 0, stream>>>(p, coords, out)
   switch (radius) {
-    case 1: lookup_fwd_kernel<1><<<grid, 256, 0, stream>>>(p, coords, out); break;
-    case 2: lookup_fwd_kernel<2><<<grid, 256, 0, stream>>>(p, coords, out); break;
-    case 3: lookup_fwd_kernel<3><<<grid, 256, 0, stream>>>(p, coords, out); break;
-    default: lookup_fwd_kernel<4><<<grid, 256, 0, stream>>>(p, coords, out); break;
+    case 1: LOOKUP_FWD(1); break;
+    case 2: LOOKUP_FWD(2); break;
+    case 3: LOOKUP_FWD(3); break;
+    default: LOOKUP_FWD(4); break;
   }
+#undef LOOKUP_FWD
   B200_LAUNCH_OK("lookup_fwd_kernel");
   return 0;
 }
