@@ -8,19 +8,22 @@
 // Here (precision TF32, the default):
 //   1. prep kernel: NCHW fp32 features -> [B][HW][Cp] (K-major) rounded to TF32 (cvt.rna), Cp = C
 //      rounded up to 32, zero padded.  7.9 MB/sample per map -- noise next to the volume.
-//   2. one persistent tcgen05 kernel.  CTA tile = 128 query pixels (M) x one 8x32 spatial patch of
-//      key pixels (N = 256), K = Cp in blocks of 32 TF32 (128-byte swizzled rows).
-//        warp 0   : TMA producer (A: [Cp,HW,B] box 32x128; B: [Cp,W,H,B] box 32x32x8), 3-stage ring
-//        warp 1   : tcgen05.mma.kind::tf32 issuer (M128 N256 K8, 4 per k-block), accumulators in
-//                   TMEM, double buffered (2 x 256 columns) so the epilogue of tile i overlaps the
-//                   MMAs of tile i+1
-//        warp 2   : TMEM allocator
-//        warps 4-11: epilogue (two warps per TMEM lane quarter, 4 patch rows each).  A query row's
-//                   8x32 patch of keys lives in the registers of two threads, so the
-//                   2x2, 4x4 and 8x8 average pools are register-local.  Level 0 goes
-//                   TMEM -> regs -> swizzled smem -> TMA store (whole 128-byte lines); levels 1-3 are
-//                   written straight from registers (64/32/16-byte runs).
+//   2. one persistent warp-specialised tcgen05 kernel.  CTA tile = 128 query pixels (M) x one 8x32
+//      spatial patch of key pixels (N = 256), K = Cp in blocks of 32 TF32 (128-byte swizzled rows).
+//        warp 0    : TMA producer (A: [Cp,HW,B] box 32x128; B: [Cp,W,H,B] box 32x32x8), 3-stage ring
+//        warp 1    : tcgen05.mma.kind::tf32 issuer (M128 N256 K8, 4 per k-block), accumulators in
+//                    TMEM, double buffered (2 x 256 columns)
+//        warp 2    : TMEM allocator
+//        warps 4-11: two independent epilogue groups (4 warps each) that own alternate tiles / TMEM
+//                    buffers.  A thread owns one query row = the whole 8x32 patch of keys, read one
+//                    patch row (32 columns) at a time with tcgen05.ld, so the 2x2, 4x4 and 8x8
+//                    average pools are register-local.  Levels 0 and 1 go through a swizzled
+//                    per-warp staging tile and leave as full 128/64-byte lines (st.global.cs);
+//                    levels 2-3 are written straight from registers.
 //      The volume is written exactly once and never re-read: 313 MB/sample instead of ~1.1 GB.
+//      Measured (profiles/): the kernel is bound by the L2 fabric -- 2.8 GB of
+//      operand re-reads at ~14 TB/s, then 1.25 GB of writes at HBM speed; a 2-CTA cluster with
+//      TMA multicast of the key patch was tried and does not reduce L2 traffic at cluster size 2.
 //   Precision FP32 (exact, also the path for W % 4 != 0): a plain SIMT tile GEMM + pooling kernels.
 //
 // Error bound of the TF32 path (documented in DESIGN.md, asserted in tests): inputs are rounded to
@@ -63,9 +66,9 @@ constexpr int PH = 8, PW = 32;  // key patch
 constexpr int NST = 3;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_ROW_BYTES = 32 * 128;                 // one TMA store box: 32 query rows x 32 floats
-constexpr int EPI_WARP_BYTES = 2 * EPI_ROW_BYTES;       // double-buffered staging of one patch row
+constexpr int EPI_WARP_BYTES = EPI_ROW_BYTES;           // per-warp staging tile: one patch row of 32 queries
 constexpr int EPI_WARPS = 8;
-constexpr int XBUF_BYTES = 2 * 4 * 32 * 16;               // level-3 exchange between the two halves
+constexpr int XBUF_BYTES = 0;
 constexpr int SMEM_BYTES = NST * STAGE_BYTES + EPI_WARPS * EPI_WARP_BYTES + XBUF_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int THREADS = 384;
 constexpr int TMEM_COLS = 512;
@@ -75,6 +78,7 @@ struct Params {
   int MT, NTY, NTX;          // tile counts
   float scale;
   int debug;                 // B200CORR_DEBUG bits (diagnostics): 1 skip level-0 stores, 2 skip pooled stores
+  float *lvl0;               // level 0
   float *lvl[3];             // levels 1..3 (nullptr if not requested)
   int LH[3], LW[3];
 };
@@ -97,7 +101,7 @@ __device__ __forceinline__ void store_row_vec(float *dst, const float (&v)[N], i
 
 __global__ void __launch_bounds__(tc::THREADS, 1)
 allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   const __grid_constant__ CUtensorMap mapC, const tc::Params p) {
+                   const tc::Params p) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle atoms
@@ -115,14 +119,13 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
-    tma_prefetch_desc(&mapC);
     for (int s = 0; s < NST; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], EPI_WARPS);
+      mbar_init(&tempty_bar[s], 4);   // the 4 warps of the epilogue group that owns this buffer
     }
     fence_barrier_init();
   }
@@ -181,72 +184,124 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue: 8 warps.  Warp w may only touch TMEM lanes 32*(w%4) .. +31; the two
-    // warps of a lane quarter split the patch rows (columns): half 0 -> rows 0-3, half 1 -> rows 4-7.
-    const int wq = warp & 3, half = (warp - 4) >> 2;
+    // ================= epilogue: two independent groups of 4 warps.  Group g owns the tiles with
+    // local index lt % 2 == g, i.e. TMEM accumulator buffer g: while one group is storing its tile
+    // the other reads the next accumulator and the MMA warp fills the buffer after that.  (With a
+    // single group the three phases ran back to back: TMEM reads queue behind the MMAs in flight.)
+    // Warp w may only touch TMEM lanes 32*(w%4) .. +31; a thread owns one query row = the whole
+    // 8x32 key patch, one patch row (32 columns) at a time, so all average pools are register-local.
+    const int wq = warp & 3, grp = (warp - 4) >> 2;
     uint8_t *ebuf = epi + (warp - 4) * EPI_WARP_BYTES;
-    float4 *xbuf = reinterpret_cast<float4 *>(epi + 8 * EPI_WARP_BYTES);  // [2][4][32] level-3 exchange
     const bool m_dbg = !(p.debug & 2);
     const bool v1 = p.lvl[0] && (p.LW[0] % 4 == 0), v2 = p.lvl[1] && (p.LW[1] % 4 == 0),
                v3 = p.lvl[2] && (p.LW[2] % 4 == 0);
-    uint32_t lt = 0, sbuf = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+    for (uint32_t lt = grp; (int)(blockIdx.x + lt * gridDim.x) < total; lt += 2) {
+      const int t = blockIdx.x + lt * gridDim.x;
       const int nt = t % NT, mt = (t / NT) % p.MT, b = t / (NT * p.MT);
       const int y0 = (nt / p.NTX) * PH, x0 = (nt % p.NTX) * PW;
-      const int mrow0 = mt * BM + wq * 32;
-      const int m = mrow0 + lane;
+      int mrow0 = mt * BM + wq * 32;
+      int m = mrow0 + lane;
       const bool m_ok = m < p.HW && m_dbg;
-      const size_t q = (size_t)b * p.HW + (m_ok ? m : 0);
-      const int buf = lt & 1;
-      mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
+      size_t q = (size_t)b * p.HW + (m_ok ? m : 0);
+      if (p.debug & 4) {   // diagnostics: every tile stores into the first 128 query rows (L2-resident)
+        mrow0 = wq * 32;
+        m = mrow0 + lane;
+        q = m;
+      }
+      const int bst = (p.debug & 4) ? 0 : b;
+      mbar_wait(&tfull_bar[grp], (lt >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(wq * 32) << 16) + half * 128;
+      const uint32_t taddr = tmem_base + grp * BN + ((uint32_t)(wq * 32) << 16);
 
-      float prev[32], p1prev[16], p2[8];
+      // global pointers of this tile (coalesced write-out: lane -> (row, 16-byte chunk))
+      float *vol0 = p.lvl0;
+      const int wrow = lane >> 3, wchunk = lane & 7;      // level 0: 4 rows x 8 chunks per instruction
+      const int xrow = lane >> 2, xchunk = lane & 3;      // level 1: 8 rows x 4 chunks per instruction
+      float prev[32], p1prev[16], p2prev[8];
 #pragma unroll
-      for (int step = 0; step < 4; ++step, sbuf ^= 1) {
-        const int r = half * 4 + step;  // patch row
+      for (int r = 0; r < PH; ++r) {
         float cur[32];
-        tmem_ld_32x32(taddr + step * 32, cur);
-        // the staging buffer written two steps ago must have been read by its TMA store
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
+        tmem_ld_32x32(taddr + r * 32, cur);
         tmem_ld_wait();
+        if (r == PH - 1) {
+          // last TMEM read of this accumulator: hand the buffer back before the math / stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) cur[i] *= p.scale;
-        // ---- level 0: one patch row -> swizzled staging -> TMA store (32 query rows x 128 B)
-        uint8_t *s0 = ebuf + sbuf * EPI_ROW_BYTES;
+        // ---- level 0: one patch row of 32 query rows -> swizzled staging -> full-line streaming stores
+        __syncwarp();   // previous readers of the staging tile are done
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int off = lane * 128 + ((j ^ (lane & 7)) << 4);
-          *reinterpret_cast<float4 *>(s0 + off) = make_float4(cur[4 * j], cur[4 * j + 1], cur[4 * j + 2], cur[4 * j + 3]);
+          *reinterpret_cast<float4 *>(ebuf + off) = make_float4(cur[4 * j], cur[4 * j + 1], cur[4 * j + 2], cur[4 * j + 3]);
         }
-        fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && !(p.debug & 1)) {
-          tma_store_4d(&mapC, s0, x0, y0 + r, mrow0, b);
-          tma_store_commit();
+        if (!(p.debug & 1)) {
+          const int y = y0 + r, x = x0 + 4 * wchunk;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + wrow;
+            const float4 v = *reinterpret_cast<const float4 *>(ebuf + row * 128 + ((wchunk ^ (row & 7)) << 4));
+            const int mm = mrow0 + row;
+            if (mm < p.HW && y < p.H && x < p.W)
+              __stcs(reinterpret_cast<float4 *>(vol0 + (((size_t)bst * p.HW + mm) * p.H + y) * p.W + x), v);
+          }
         }
-        if (step & 1) {
-          // ---- level 1: 2x2 means of rows (r-1, r) -> 16 values
+        if (r & 1) {
+          // ---- level 1: 2x2 means of rows (r-1, r) -> 16 values per query row
           float p1[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             p1[j] = (((prev[2 * j] + prev[2 * j + 1]) + cur[2 * j]) + cur[2 * j + 1]) * 0.25f;
-          if (p.lvl[0] && m_ok) {
+          if (p.lvl[0] && m_dbg) {
             const int y1 = y0 / 2 + (r >> 1), x1 = x0 / 2;
-            if (y1 < p.LH[0])
-              store_row_vec(p.lvl[0] + (q * p.LH[0] + y1) * p.LW[0] + x1, p1, x1, p.LW[0], v1);
+            if (v1) {
+              // staged like level 0: [32 rows][64 B], chunk swizzled by (row >> 1) & 3
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4 *>(ebuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                    make_float4(p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int row = it * 8 + xrow;
+                const float4 v = *reinterpret_cast<const float4 *>(ebuf + row * 64 + ((xchunk ^ ((row >> 1) & 3)) << 4));
+                const int mm = mrow0 + row, xx = x1 + 4 * xchunk;
+                if (mm < p.HW && y1 < p.LH[0] && xx < p.LW[0])
+                  __stcs(reinterpret_cast<float4 *>(p.lvl[0] + (((size_t)bst * p.HW + mm) * p.LH[0] + y1) * p.LW[0] + xx), v);
+              }
+            } else if (m_ok && y1 < p.LH[0]) {
+              store_row_vec(p.lvl[0] + (q * p.LH[0] + y1) * p.LW[0] + x1, p1, x1, p.LW[0], false);
+            }
           }
-          if (step == 3) {
-            // ---- level 2: means of the two level-1 rows of this half -> 8 values
+          if ((r & 3) == 3) {
+            // ---- level 2: means of two level-1 rows -> 8 values
+            float p2[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               p2[j] = (((p1prev[2 * j] + p1prev[2 * j + 1]) + p1[2 * j]) + p1[2 * j + 1]) * 0.25f;
             if (p.lvl[1] && m_ok) {
-              const int y2 = y0 / 4 + half, x2 = x0 / 4;
+              const int y2 = y0 / 4 + (r >> 2), x2 = x0 / 4;
               if (y2 < p.LH[1])
                 store_row_vec(p.lvl[1] + (q * p.LH[1] + y2) * p.LW[1] + x2, p2, x2, p.LW[1], v2);
+            }
+            if (r == 7) {
+              float p3[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                p3[j] = (((p2prev[2 * j] + p2prev[2 * j + 1]) + p2[2 * j]) + p2[2 * j + 1]) * 0.25f;
+              if (p.lvl[2] && m_ok) {
+                const int y3 = y0 / 8, x3 = x0 / 8;
+                if (y3 < p.LH[2])
+                  store_row_vec(p.lvl[2] + (q * p.LH[2] + y3) * p.LW[2] + x3, p3, x3, p.LW[2], v3);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) p2prev[j] = p2[j];
             }
           } else {
 #pragma unroll
@@ -257,30 +312,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           for (int i = 0; i < 32; ++i) prev[i] = cur[i];
         }
       }
-      // all TMEM reads of this accumulator buffer are done: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-      // ---- level 3: the 8x8 mean needs the level-2 rows of both halves -> exchange through smem
-      float4 *xs = xbuf + ((lt & 1) * 4 + wq) * 32 + lane;
-      if (half == 0)
-        *xs = make_float4(p2[0] + p2[1], p2[2] + p2[3], p2[4] + p2[5], p2[6] + p2[7]);
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
-      if (half == 1) {
-        const float4 h = *xs;
-        float p3[4];
-        p3[0] = ((h.x + p2[0]) + p2[1]) * 0.25f;
-        p3[1] = ((h.y + p2[2]) + p2[3]) * 0.25f;
-        p3[2] = ((h.z + p2[4]) + p2[5]) * 0.25f;
-        p3[3] = ((h.w + p2[6]) + p2[7]) * 0.25f;
-        if (p.lvl[2] && m_ok) {
-          const int y3 = y0 / 8, x3 = x0 / 8;
-          if (y3 < p.LH[2])
-            store_row_vec(p.lvl[2] + (q * p.LH[2] + y3) * p.LW[2] + x3, p3, x3, p.LW[2], v3);
-        }
-      }
     }
-    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -407,7 +439,7 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
     prep_kmajor_tf32_kernel<<<pgrid, 256, 0, stream>>>(f2, f2t, C, Cp, HW);
     B200_LAUNCH_OK("prep_kmajor_tf32_kernel");
 
-    CUtensorMap mapA, mapB, mapC;
+    CUtensorMap mapA, mapB;
     {
       const uint64_t dims[3] = {(uint64_t)Cp, (uint64_t)HW, (uint64_t)B};
       const uint64_t str[3] = {4, (uint64_t)Cp * 4, (uint64_t)HW * Cp * 4};
@@ -424,20 +456,13 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
         return e;
     }
-    {
-      const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)HW, (uint64_t)B};
-      const uint64_t str[4] = {4, (uint64_t)W * 4, (uint64_t)HW * 4, (uint64_t)HW * HW * 4};
-      const uint32_t box[4] = {tc::PW, 1, 32, 1};
-      if (int e = b200::make_tensor_map(&mapC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, h_levels[0], dims, str,
-                                        box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE))
-        return e;
-    }
     tc::Params p;
     p.B = B; p.HW = HW; p.H = H; p.W = W; p.KB = Cp / 32;
     p.MT = (HW + tc::BM - 1) / tc::BM;
     p.NTY = (H + tc::PH - 1) / tc::PH;
     p.NTX = (W + tc::PW - 1) / tc::PW;
     p.scale = scale;
+    p.lvl0 = h_levels[0];
     {
       const char *dbg = getenv("B200CORR_DEBUG");
       p.debug = dbg ? atoi(dbg) : 0;
@@ -458,7 +483,7 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
     }
     const int total = B * p.MT * p.NTY * p.NTX;
     const int grid = total < b200::num_sms() ? total : b200::num_sms();
-    allpairs_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(mapA, mapB, mapC, p);
+    allpairs_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(mapA, mapB, p);
     B200_LAUNCH_OK("allpairs_tc_kernel");
   }
   for (int l = first_unpooled; l < num_levels; ++l)

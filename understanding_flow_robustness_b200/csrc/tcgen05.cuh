@@ -66,6 +66,34 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                : "memory");
 }
 
+// same, but the arrival is multicast to the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t *bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+// ---- thread-block clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load multicast to the same smem offset (and mbarrier offset) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_4d_multicast(void *dst, const CUtensorMap *m, uint64_t *bar,
+                                                      int c0, int c1, int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+
 // ---- TMEM -> registers: this warp's 32 lanes x 32 consecutive columns
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&r)[32]) {
   uint32_t u[32];
