@@ -63,7 +63,7 @@ prep_kmajor_tf32_kernel(const float *__restrict__ in, float *__restrict__ out, i
 namespace tc {
 constexpr int BM = 128, BN = 256, BK = 32;
 constexpr int PH = 8, PW = 32;  // key patch
-constexpr int NST = 3;
+constexpr int NST = 4;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_ROW_BYTES = 32 * 128;                 // one TMA store box: 32 query rows x 32 floats
 constexpr int EPI_WARP_BYTES = EPI_ROW_BYTES;           // per-warp staging tile: one patch row of 32 queries
