@@ -78,6 +78,9 @@ FAST_CASES = [
     (1, 128, 10, 24, 9, 1),      # PWC-Net structure
     (2, 8, 7, 12, 9, 1),
     (1, 128, 3, 8, 21, 2),       # image smaller than the patch radius
+    (2, 96, 12, 40, 9, 1),       # PWC-Net level: C % 32 == 0 backward (2 channels per thread)
+    (1, 32, 24, 80, 9, 1),
+    (1, 64, 13, 24, 21, 2),      # patch 21 with the 32-channel unit
 ]
 
 

@@ -34,10 +34,10 @@ constexpr int odd4b(int x) {
 }
 constexpr int round_up_c(int a, int b) { return (a + b - 1) / b * b; }
 
-template <int PH_, int PW_, int DPW_, int WHICH_>
+template <int PH_, int PW_, int DPW_, int WHICH_, int NCH_ = 8>
 struct BwdCfg {
   static constexpr int PH = PH_, PW = PW_, DPW = DPW_, WHICH = WHICH_;
-  static constexpr int T = 8, NCH = 8, CGROUPS = 4;
+  static constexpr int T = 8, NCH = NCH_, CGROUPS = 4;
   static constexpr int CH_UNIT = 16 * NCH;            // 128 channels per unit (16 channel lanes x NCH)
   static constexpr int COLS = CGROUPS * T;            // 32 pixels per unit row
   static constexpr int RH = (PH - 1) / 2, RW = (PW - 1) / 2;
@@ -415,18 +415,28 @@ int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, 
 
 namespace b200 {
 
+// channels per unit: 128 (8 per thread) when C allows, else 32 (2 per thread: PWC-Net's 96/64/32)
+#define B200_BWD_DISPATCH(FN, ...)                                                         \
+  do {                                                                                     \
+    if (patchH == 21 && patchW == 21 && dpW == 2) {                                         \
+      if (C % 128 == 0) { FN(21, 21, 2, 8, __VA_ARGS__); } else { FN(21, 21, 2, 2, __VA_ARGS__); } \
+    } else if (patchH == 9 && patchW == 9 && dpW == 1) {                                    \
+      if (C % 128 == 0) { FN(9, 9, 1, 8, __VA_ARGS__); } else { FN(9, 9, 1, 2, __VA_ARGS__); }     \
+    }                                                                                      \
+  } while (0)
+
 int sampler_fast_backward(const float *in1, const float *in2, const float *gout, float *gin1,
                           float *gin2, int B, int C, int H, int W, const int *q, const int *plan,
                           cudaStream_t stream) {
   const int patchH = q[2], patchW = q[3], dpH = q[8], dpW = q[9];
-  if (patchH == 21 && patchW == 21 && dpW == 2) {
-    if (int e = launch_bwd<BwdCfg<21, 21, 2, 1>>(in2, gout, gin1, B, C, H, W, dpH, plan, stream)) return e;
-    return launch_bwd<BwdCfg<21, 21, 2, 2>>(in1, gout, gin2, B, C, H, W, dpH, plan, stream);
+#define RUN(PH, PW, DP, N, dummy)                                                                     \
+  {                                                                                                   \
+    if (int e = launch_bwd<BwdCfg<PH, PW, DP, 1, N>>(in2, gout, gin1, B, C, H, W, dpH, plan, stream)) \
+      return e;                                                                                       \
+    return launch_bwd<BwdCfg<PH, PW, DP, 2, N>>(in1, gout, gin2, B, C, H, W, dpH, plan, stream);      \
   }
-  if (patchH == 9 && patchW == 9 && dpW == 1) {
-    if (int e = launch_bwd<BwdCfg<9, 9, 1, 1>>(in2, gout, gin1, B, C, H, W, dpH, plan, stream)) return e;
-    return launch_bwd<BwdCfg<9, 9, 1, 2>>(in1, gout, gin2, B, C, H, W, dpH, plan, stream);
-  }
+  B200_BWD_DISPATCH(RUN, 0);
+#undef RUN
   set_error("sampler_fast_backward: no instantiation for patch %dx%d dilation_patch_w %d", patchH,
             patchW, dpW);
   return -1;
@@ -435,9 +445,11 @@ int sampler_fast_backward(const float *in1, const float *in2, const float *gout,
 // number of ints of the backward plan (0 if the problem has no units)
 size_t sampler_fast_backward_plan_ints(int B, int C, int H, int W, const int *q) {
   BwdParams p;
-  const int patchH = q[2];
-  int e = patchH == 21 ? bwd_geometry<BwdCfg<21, 21, 2, 1>>(p, B, C, H, W, q[8])
-                       : bwd_geometry<BwdCfg<9, 9, 1, 1>>(p, B, C, H, W, q[8]);
+  const int patchH = q[2], patchW = q[3], dpW = q[9];
+  int e = -1;
+#define GEO(PH, PW, DP, N, dummy) e = bwd_geometry<BwdCfg<PH, PW, DP, 1, N>>(p, B, C, H, W, q[8]);
+  B200_BWD_DISPATCH(GEO, 0);
+#undef GEO
   if (e || p.total_units == 0) return 0;
   return (size_t)bwd_grid(p.total_units) + 1 + p.total_units;
 }
@@ -445,13 +457,16 @@ size_t sampler_fast_backward_plan_ints(int B, int C, int H, int W, const int *q)
 int sampler_fast_backward_plan(int B, int C, int H, int W, const int *q, int *h_plan, size_t bytes) {
   const size_t n = sampler_fast_backward_plan_ints(B, C, H, W, q);
   if (n == 0) return 0;
+  const int patchH = q[2], patchW = q[3], dpW = q[9];
   BwdParams p;
-  if (q[2] == 21) {
-    bwd_geometry<BwdCfg<21, 21, 2, 1>>(p, B, C, H, W, q[8]);
-    return bwd_plan<BwdCfg<21, 21, 2, 1>>(B, C, H, W, q[8], bwd_grid(p.total_units), h_plan, bytes);
+#define PLAN(PH, PW, DP, N, dummy)                                                                  \
+  {                                                                                                 \
+    bwd_geometry<BwdCfg<PH, PW, DP, 1, N>>(p, B, C, H, W, q[8]);                                    \
+    return bwd_plan<BwdCfg<PH, PW, DP, 1, N>>(B, C, H, W, q[8], bwd_grid(p.total_units), h_plan, bytes); \
   }
-  bwd_geometry<BwdCfg<9, 9, 1, 1>>(p, B, C, H, W, q[8]);
-  return bwd_plan<BwdCfg<9, 9, 1, 1>>(B, C, H, W, q[8], bwd_grid(p.total_units), h_plan, bytes);
+  B200_BWD_DISPATCH(PLAN, 0);
+#undef PLAN
+  return -1;
 }
 
 // The structure the register-blocked kernels cover (everything else runs on sampler_generic.cu).
@@ -468,7 +483,7 @@ bool sampler_fast_applicable(int B, int C, int H, int W, const int *q, int dtype
   int ng = 0;
   for (int rp = 0; rp < dpH; ++rp) ng += (sublattice_rows(H, dpH, rp) + kRowsPerGroup - 1) / kRowsPerGroup;
   if (ng > kSamplerMaxGroups) return false;
-  if (backward) return C % 128 == 0;
+  if (backward) return C % 32 == 0;
   return C % 8 == 0;
 }
 
