@@ -365,14 +365,14 @@ def attack_bench(dev, rank, world, global_batch):
     from understanding_flow_robustness_b200 import attack
     from understanding_flow_robustness_b200.harness import FlowNetCHarness
     torch.manual_seed(0)                                   # same weights / patch on every rank
-    net = FlowNetCHarness().to(dev).eval()
+    net = FlowNetCHarness().to(dev).eval().to(memory_format=torch.channels_last)   # cuDNN's preferred conv layout
     for q in net.parameters():
         q.requires_grad_(False)
     H, W, p = 384, 1280, 100
     idx = attack.shard_slice(global_batch, rank, world)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
-    i1 = torch.rand(len(idx), 3, H, W, device=dev, generator=g)
-    i2 = torch.rand(len(idx), 3, H, W, device=dev, generator=g)
+    i1 = torch.rand(len(idx), 3, H, W, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
+    i2 = torch.rand(len(idx), 3, H, W, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
     patch = torch.rand(1, 3, p, p, device=dev)
     mask = attack.circle_mask(p, dev)
     cfg = attack.PatchAttackConfig()

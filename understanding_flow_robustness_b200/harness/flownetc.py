@@ -17,8 +17,10 @@ from ..spatial_correlation_sampler import spatial_correlation_sample
 
 def correlate(input1, input2):
     """models/submodules.py:124-138: patch 21, dilation_patch 2, collapsed to (B, 441, H, W), / C."""
-    out = spatial_correlation_sample(input1, input2, kernel_size=1, patch_size=21, stride=1, padding=0,
-                                     dilation_patch=2)
+    # the operator wants dense NCHW (CHECK_CONTIGUOUS in the reference); a channels-last conv stack
+    # pays one layout copy here
+    out = spatial_correlation_sample(input1.contiguous(), input2.contiguous(), kernel_size=1, patch_size=21,
+                                     stride=1, padding=0, dilation_patch=2)
     b, ph, pw, h, w = out.size()
     return out.view(b, ph * pw, h, w) / input1.size(1)
 
