@@ -75,6 +75,7 @@ struct FwdCfg {
 
 struct FwdParams {
   int B, C, H, W, dpH, NG, total_units;
+  int wide_store;   // W % 8 == 0 and a 32-byte aligned output: one STG.256 per 8-pixel run
   b200::SamplerGroups g;
 };
 
@@ -117,6 +118,12 @@ __device__ __forceinline__ void decode_unit(const FwdParams &p, int u, Unit &x) 
 
 __device__ __forceinline__ void stg128(float *p, float a, float b, float c, float d) {
   *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+// 256-bit global store (sm_100: STG.E.256), p must be 32-byte aligned
+__device__ __forceinline__ void stg256(float *p, float2 a, float2 b, float2 c, float2 d) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(b.x),
+               "f"(b.y), "f"(c.x), "f"(c.y), "f"(d.x), "f"(d.y)
+               : "memory");
 }
 
 template <class Cfg>
@@ -264,10 +271,17 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
       const int w0 = g * Cfg::T;
       const bool lo_ok = w0 < p.W, hi_ok = w0 + 4 < p.W;
       float *o = out + (((size_t)x.n * PH + (e + Cfg::RH)) * PW) * HW + (size_t)h * p.W + w0;
+      // one 32-byte sector per (displacement, pixel row): a single 256-bit store when rows are 32-B aligned
+      const bool wide = p.wide_store && hi_ok;
+      if (wide) {
 #pragma unroll
-      for (int k = 0; k < PW; ++k) {
-        if (lo_ok) stg128(o + k * HW, acc2[0][k].x, acc2[0][k].y, acc2[1][k].x, acc2[1][k].y);
-        if (hi_ok) stg128(o + k * HW + 4, acc2[2][k].x, acc2[2][k].y, acc2[3][k].x, acc2[3][k].y);
+        for (int k = 0; k < PW; ++k) stg256(o + k * HW, acc2[0][k], acc2[1][k], acc2[2][k], acc2[3][k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < PW; ++k) {
+          if (lo_ok) stg128(o + k * HW, acc2[0][k].x, acc2[0][k].y, acc2[1][k].x, acc2[1][k].y);
+          if (hi_ok) stg128(o + k * HW + 4, acc2[2][k].x, acc2[2][k].y, acc2[3][k].x, acc2[3][k].y);
+        }
       }
       // displacement planes whose in2 row lies outside the image are zero; the valid lanes of this
       // pixel row share them out by their rank among the valid rows
@@ -277,9 +291,14 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
       for (int qq = e + Cfg::RH - below; qq < below + above; qq += nvalid) {
         const int phc = qq < below ? qq : PH - above + (qq - below);
         float *z = out + (((size_t)x.n * PH + phc) * PW) * HW + (size_t)h * p.W + w0;
+        const float2 zz = make_float2(0.f, 0.f);
         for (int k = 0; k < PW; ++k) {
-          if (lo_ok) stg128(z + k * HW, 0.f, 0.f, 0.f, 0.f);
-          if (hi_ok) stg128(z + k * HW + 4, 0.f, 0.f, 0.f, 0.f);
+          if (wide) {
+            stg256(z + k * HW, zz, zz, zz, zz);
+          } else {
+            if (lo_ok) stg128(z + k * HW, 0.f, 0.f, 0.f, 0.f);
+            if (hi_ok) stg128(z + k * HW + 4, 0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
     }
@@ -292,6 +311,7 @@ int launch_fwd(const float *in1, const float *in2, float *out, int B, int C, int
   FwdParams p;
   p.B = B; p.C = C; p.H = H; p.W = W; p.dpH = dpH;
   p.NG = (W + Cfg::T - 1) / Cfg::T;
+  p.wide_store = (W % 8 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
   int ng = 0, units = 0;
   for (int rp = 0; rp < dpH; ++rp) {
     const int NS = b200::sublattice_rows(H, dpH, rp);
