@@ -63,6 +63,7 @@ struct BwdCfg {
 struct BwdParams {
   const int *plan;   // optional LPT schedule: [grid+1] offsets then unit ids (device memory), or nullptr
   int B, C, H, W, dpH, NCT, NCB, total_units;
+  int wide_store;   // W % 8 == 0 and 32-byte aligned gradient: 256-bit stores
   b200::SamplerGroups g;   // prefix[] unused here (every group has NCT*NCB units)
 };
 
@@ -160,7 +161,7 @@ __device__ __forceinline__ void bwd_pass(float2 (&acc2)[Cfg::T / 2][Cfg::NCH], c
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(288, 1)
 sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_constant__ CUtensorMap map_g,
                    float *__restrict__ gin, const BwdParams p) {
   constexpr int NST = Cfg::NST, RH = Cfg::RH, PW = Cfg::PW, NC = Cfg::NC, T = Cfg::T;
@@ -201,7 +202,7 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
   // ---- producer (thread 0): walks (unit, source row) NST-1 steps ahead of the math
   int pu = it_begin, ps = 0;
   uint32_t pq = 0;
-  if (tid == 0 && pu < nunits) decode_bunit<Cfg>(p, ulist ? ulist[pu] : pu, px);
+  if (tid == 256 && pu < nunits) decode_bunit<Cfg>(p, ulist ? ulist[pu] : pu, px);
   auto issue = [&]() {
     if (pu >= nunits) return;
     const int st = pq % NST;
@@ -238,8 +239,16 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
       if (pu < nunits) decode_bunit<Cfg>(p, ulist ? ulist[pu] : pu, px);
     }
   };
-  if (tid == 0)
-    for (int s = 0; s < NST - 1; ++s) issue();
+  if (warp == 8) {
+    // ---- dedicated producer warp: one lane walks every (unit, source row) of this CTA, NST deep
+    if (lane == 0) {
+      for (uint32_t n = 0; pu < nunits; ++n) {
+        if (n >= (uint32_t)NST) mbar_wait(&empty_bar[n % NST], ((n / NST) - 1) & 1);
+        issue();
+      }
+    }
+    return;
+  }
 
   uint32_t q = 0;
   for (int ui = it_begin; ui < nunits; ui += it_step) {
@@ -259,10 +268,6 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
 
     for (int step = 0; step < x.nsteps; ++step, ++q) {
       const int st = q % NST;
-      if (tid == 0) {
-        if (q > 0) mbar_wait(&empty_bar[(q - 1) % NST], ((q - 1) / NST) & 1);
-        issue();
-      }
       mbar_wait(&full_bar[st], (q / NST) & 1);
       const int R = x.Rlo + step;
       const int e = Cfg::WHICH == 1 ? R - s : s - R;
@@ -283,6 +288,14 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
       const size_t HW = (size_t)p.H * p.W;
       float *o = gin + ((size_t)x.n * p.C + x.cb * Cfg::CH_UNIT + lj) * HW +
                  (size_t)h * p.W + x0;
+      if (p.wide_store && x0 + 4 < p.W) {
+#pragma unroll
+        for (int ci = 0; ci < Cfg::NCH; ++ci)   // one 32-byte sector per (channel, row): STG.256
+          asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + (size_t)ci * 16 * HW),
+                       "f"(acc[0][ci].x), "f"(acc[0][ci].y), "f"(acc[1][ci].x), "f"(acc[1][ci].y),
+                       "f"(acc[2][ci].x), "f"(acc[2][ci].y), "f"(acc[3][ci].x), "f"(acc[3][ci].y)
+                       : "memory");
+      } else
 #pragma unroll
       for (int ci = 0; ci < Cfg::NCH; ++ci) {
         if (x0 < p.W)
@@ -301,6 +314,7 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
 template <class Cfg>
 int bwd_geometry(BwdParams &p, int B, int C, int H, int W, int dpH) {
   p.plan = nullptr;
+  p.wide_store = 0;
   p.B = B; p.C = C; p.H = H; p.W = W; p.dpH = dpH;
   p.NCT = (W + Cfg::COLS - 1) / Cfg::COLS;
   p.NCB = C / Cfg::CH_UNIT;
@@ -376,6 +390,7 @@ int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, 
   BwdParams p;
   if (int e = bwd_geometry<Cfg>(p, B, C, H, W, dpH)) return e;
   p.plan = plan;
+  p.wide_store = (W % 8 == 0 && ((uintptr_t)gin & 31) == 0) ? 1 : 0;
   if (p.total_units == 0) return 0;
 
   CUtensorMap map_o, map_g;
@@ -406,7 +421,7 @@ int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, 
     attr_done = true;
   }
   const int grid = bwd_grid(p.total_units);
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(map_o, map_g, gin, p);
+  kern<<<grid, 288, Cfg::SMEM_BYTES, stream>>>(map_o, map_g, gin, p);
   B200_LAUNCH_OK(Cfg::WHICH == 1 ? "sampler_bwd_kernel<gIn1>" : "sampler_bwd_kernel<gIn2>");
   return 0;
 }
