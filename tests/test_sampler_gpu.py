@@ -176,3 +176,25 @@ def test_error_behaviour():
         spatial_correlation_sample(c, c[:, :2].contiguous(), 1, 3)   # shape mismatch
     out = spatial_correlation_sample(c[:0], c[:0], 1, 3)  # empty batch
     assert out.shape == (0, 3, 3, 8, 8)
+
+
+def test_second_device_in_the_same_process():
+    """check.py:62-73 runs the op on every visible GPU from one process."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle import sampler_oracle
+    from understanding_flow_robustness_b200 import CorrBlock, coords_grid, spatial_correlation_sample
+    rng = np.random.default_rng(3)
+    in1 = rng.standard_normal((1, 128, 12, 32)).astype(np.float32)
+    in2 = rng.standard_normal((1, 128, 12, 32)).astype(np.float32)
+    ref = sampler_oracle.forward(in1, in2, 1, 21, 1, 0, 1, 2)
+    for dev in ("cuda:0", "cuda:1"):
+        a = torch.from_numpy(in1).to(dev).requires_grad_()
+        b = torch.from_numpy(in2).to(dev)
+        out = spatial_correlation_sample(a, b, 1, 21, 1, 0, 1, 2)
+        out.sum().backward()
+        assert out.device == a.device
+        assert _rel(out.detach().cpu().numpy(), ref) <= 1e-5
+        f = torch.randn(1, 32, 8, 32, device=dev)
+        blk = CorrBlock(f, f, 2, 2)
+        assert blk(coords_grid(1, 8, 32, dev)).device == f.device

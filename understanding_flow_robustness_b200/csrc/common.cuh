@@ -48,6 +48,10 @@ static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; 
 
 int num_sms();  // SM count of the current device (cached)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device and serialises with running work:
+// call it once per (kernel, device).  `done` is a zero-initialised per-kernel flag array.
+int set_max_smem_once(const void *kernel, int bytes, bool (&done)[64]);
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time).
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1 (dim 0 is contiguous).
 int make_tensor_map(CUtensorMap *map, CUtensorMapDataType dtype, int rank, const void *base,

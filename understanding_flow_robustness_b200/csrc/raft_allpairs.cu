@@ -475,12 +475,8 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
       if (want) B200_CHECK(((uintptr_t)h_levels[l + 1] & 15) == 0, "allpairs_pyramid: level %d misaligned", l + 1);
     }
     first_unpooled = 4;
-    static bool attr_done = false;  // one process per GPU: set once, not on every launch
-    if (!attr_done) {
-      B200_CUDA(cudaFuncSetAttribute(allpairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     tc::SMEM_BYTES));
-      attr_done = true;
-    }
+    static bool attr_done[64] = {};  // per device
+    if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel, tc::SMEM_BYTES, attr_done)) return e;
     const int total = B * p.MT * p.NTY * p.NTX;
     const int grid = total < b200::num_sms() ? total : b200::num_sms();
     allpairs_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(mapA, mapB, p);

@@ -415,11 +415,8 @@ int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, 
       return e;
   }
   auto kern = sampler_bwd_kernel<Cfg>;
-  static bool attr_done = false;  // one process per GPU: set once, not on every launch
-  if (!attr_done) {
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  static bool attr_done[64] = {};  // per (kernel instantiation, device)
+  if (int e = b200::set_max_smem_once((const void *)kern, Cfg::SMEM_BYTES, attr_done)) return e;
   const int grid = bwd_grid(p.total_units);
   kern<<<grid, 288, Cfg::SMEM_BYTES, stream>>>(map_o, map_g, gin, p);
   B200_LAUNCH_OK(Cfg::WHICH == 1 ? "sampler_bwd_kernel<gIn1>" : "sampler_bwd_kernel<gIn2>");

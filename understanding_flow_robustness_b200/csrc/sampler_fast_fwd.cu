@@ -349,11 +349,8 @@ int launch_fwd(const float *in1, const float *in2, float *out, int B, int C, int
     return e;
 
   auto kern = sampler_fwd_kernel<Cfg>;
-  static bool attr_done = false;  // one process per GPU: set once, not on every launch
-  if (!attr_done) {
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  static bool attr_done[64] = {};  // per (kernel instantiation, device)
+  if (int e = b200::set_max_smem_once((const void *)kern, Cfg::SMEM_BYTES, attr_done)) return e;
   const int grid = p.total_units < b200::num_sms() ? p.total_units : b200::num_sms();
   kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(map1, map2, out, p);
   B200_LAUNCH_OK("sampler_fwd_kernel");
