@@ -10,8 +10,8 @@
 // The reference stages 32-channel tiles of both maps per 4x8 query block and loops the (2r+2)^2
 // window serially with one barrier per window point.  Here one warp owns one query: the query's
 // feature vector lives in registers (lane = channel slice), every window pixel of fmap2 is one
-// fully coalesced C*4-byte read (NHWC), the (2r+2)^2 partial dot products stay in registers and
-// are reduced across lanes once at the end through a padded shared-memory transpose; the 8 queries
+// fully coalesced C*4-byte read (NHWC), the partial dot products of one window row at a time go to a
+// padded per-warp shared tile and are reduced across lanes once at the end; the 8 queries
 // of a CTA then write their (2r+1)^2 outputs as 32-byte sectors.
 #include "common.cuh"
 
@@ -33,7 +33,8 @@ altcorr_fwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2,
                    const float *__restrict__ coords, float *__restrict__ corr, int B, int N, int H1,
                    int W1, int H2, int W2, int C) {
   using G = AGeo<R>;
-  __shared__ float red[8][32][33];
+  // per-warp [window column][lane] partial sums of ONE window row (pitch 33: conflict-free both ways)
+  __shared__ float red[8][G::WN][33];
   __shared__ float S[8][G::NCHUNK * 32];
   __shared__ float O[G::RD * G::RD][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -62,16 +63,21 @@ altcorr_fwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2,
   if (!(fabsf(fyf) < 1e8f)) fyf = -1e8f;
   const int fx = (int)fxf, fy = (int)fyf;
 
-  float acc[G::NW];
-#pragma unroll
+  // one window row at a time (a real loop: the fully unrolled 100-pixel version thrashed the
+  // instruction cache): WN coalesced pixel reads, then the row's partial dot products are reduced
+  // across lanes through the per-warp tile (lane l < WN sums column l)
+#pragma unroll 1
   for (int iy = 0; iy < G::WN; ++iy) {
     const int y2 = fy - R + iy;
+    const bool row_ok = q_ok && y2 >= 0 && y2 < H2;
+    const float4 *prow = reinterpret_cast<const float4 *>(f2 + (((size_t)b * H2 + (row_ok ? y2 : 0)) * W2) * C);
+    float acc[G::WN];
 #pragma unroll
     for (int ix = 0; ix < G::WN; ++ix) {
       const int x2 = fx - R + ix;
       float s = 0.f;
-      if (q_ok && y2 >= 0 && y2 < H2 && x2 >= 0 && x2 < W2) {
-        const float4 *p2 = reinterpret_cast<const float4 *>(f2 + (((size_t)b * H2 + y2) * W2 + x2) * C);
+      if (row_ok && x2 >= 0 && x2 < W2) {
+        const float4 *p2 = prow + (size_t)x2 * nvec;
 #pragma unroll
         for (int i = 0; i < NV; ++i)
           if (lane + 32 * i < nvec) {
@@ -82,24 +88,20 @@ altcorr_fwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2,
             s = fmaf(a[i].w, v.w, s);
           }
       }
-      acc[iy * G::WN + ix] = s;
+      acc[ix] = s;
     }
-  }
-  // cross-lane reduction, 32 window points at a time: lane l ends up with the sum of point 32c + l
+    __syncwarp();   // previous row's readers are done with the tile
 #pragma unroll
-  for (int c = 0; c < G::NCHUNK; ++c) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c * 32 + j < G::NW) red[warp][j][lane] = acc[c * 32 + j];
+    for (int ix = 0; ix < G::WN; ++ix) red[warp][ix][lane] = acc[ix];
     __syncwarp();
-    float s = 0.f;
-    if (c * 32 + lane < G::NW) {
+    if (lane < G::WN) {
+      float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) s += red[warp][lane][j];
+      S[warp][iy * G::WN + lane] = s;
     }
-    S[warp][c * 32 + lane] = s;
-    __syncwarp();
   }
+  __syncwarp();
   // bilinear combination -> (2r+1)^2 outputs, channel = ix * RD + iy
   for (int k = lane; k < G::RD * G::RD; k += 32) {
     const int ix = k / G::RD, iy = k - ix * G::RD;
@@ -195,22 +197,23 @@ int check_alt(const char *who, int B, int N, int H1, int W1, int H2, int W2, int
   return 0;
 }
 
-#define ALT_DISPATCH(KERNEL, ...)                                                           \
+#define ALT_DISPATCH(KERNEL, SMEM, ...)                                                         \
   do {                                                                                      \
     const int nv = (C / 4 + 31) / 32;                                                       \
+    const size_t smem = (SMEM);                                                             \
     switch (radius * 8 + nv) {                                                              \
-      case 1 * 8 + 1: KERNEL<1, 1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-      case 1 * 8 + 2: KERNEL<1, 2><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-      case 1 * 8 + 3: case 1 * 8 + 4: KERNEL<1, 4><<<grid, 256, 0, stream>>>(__VA_ARGS__); break; \
-      case 2 * 8 + 1: KERNEL<2, 1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-      case 2 * 8 + 2: KERNEL<2, 2><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-      case 2 * 8 + 3: case 2 * 8 + 4: KERNEL<2, 4><<<grid, 256, 0, stream>>>(__VA_ARGS__); break; \
-      case 3 * 8 + 1: KERNEL<3, 1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-      case 3 * 8 + 2: KERNEL<3, 2><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-      case 3 * 8 + 3: case 3 * 8 + 4: KERNEL<3, 4><<<grid, 256, 0, stream>>>(__VA_ARGS__); break; \
-      case 4 * 8 + 1: KERNEL<4, 1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-      case 4 * 8 + 2: KERNEL<4, 2><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-      default: KERNEL<4, 4><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;                  \
+      case 1 * 8 + 1: KERNEL<1, 1><<<grid, 256, smem, stream>>>(__VA_ARGS__); break;           \
+      case 1 * 8 + 2: KERNEL<1, 2><<<grid, 256, smem, stream>>>(__VA_ARGS__); break;           \
+      case 1 * 8 + 3: case 1 * 8 + 4: KERNEL<1, 4><<<grid, 256, smem, stream>>>(__VA_ARGS__); break; \
+      case 2 * 8 + 1: KERNEL<2, 1><<<grid, 256, smem, stream>>>(__VA_ARGS__); break;           \
+      case 2 * 8 + 2: KERNEL<2, 2><<<grid, 256, smem, stream>>>(__VA_ARGS__); break;           \
+      case 2 * 8 + 3: case 2 * 8 + 4: KERNEL<2, 4><<<grid, 256, smem, stream>>>(__VA_ARGS__); break; \
+      case 3 * 8 + 1: KERNEL<3, 1><<<grid, 256, smem, stream>>>(__VA_ARGS__); break;           \
+      case 3 * 8 + 2: KERNEL<3, 2><<<grid, 256, smem, stream>>>(__VA_ARGS__); break;           \
+      case 3 * 8 + 3: case 3 * 8 + 4: KERNEL<3, 4><<<grid, 256, smem, stream>>>(__VA_ARGS__); break; \
+      case 4 * 8 + 1: KERNEL<4, 1><<<grid, 256, smem, stream>>>(__VA_ARGS__); break;           \
+      case 4 * 8 + 2: KERNEL<4, 2><<<grid, 256, smem, stream>>>(__VA_ARGS__); break;           \
+      default: KERNEL<4, 4><<<grid, 256, smem, stream>>>(__VA_ARGS__); break;                  \
     }                                                                                       \
   } while (0)
 
@@ -227,7 +230,7 @@ int b200corr_altcorr_forward(const float *fmap1, const float *fmap2, const float
   B200_CHECK(fmap1 && fmap2 && coords && corr, "altcorr_forward: null pointer");
   B200_CHECK((((uintptr_t)fmap1 | (uintptr_t)fmap2) & 15) == 0, "altcorr_forward: feature maps must be 16-byte aligned");
   dim3 grid((H1 * W1 + 7) / 8, N, B);
-  ALT_DISPATCH(altcorr_fwd_kernel, fmap1, fmap2, coords, corr, B, N, H1, W1, H2, W2, C);
+  ALT_DISPATCH(altcorr_fwd_kernel, 0, fmap1, fmap2, coords, corr, B, N, H1, W1, H2, W2, C);
   B200_LAUNCH_OK("altcorr_fwd_kernel");
   return 0;
 }
@@ -247,7 +250,7 @@ int b200corr_altcorr_backward(const float *fmap1, const float *fmap2, const floa
   if (coords_grad)  // the reference allocates zeros and never writes them (correlation_kernel.cu:307)
     B200_CUDA(cudaMemsetAsync(coords_grad, 0, sizeof(float) * (size_t)B * N * H1 * W1 * 2, stream));
   dim3 grid((H1 * W1 + 7) / 8, 1, B);
-  ALT_DISPATCH(altcorr_bwd_kernel, fmap1, fmap2, coords, corr_grad, fmap1_grad, fmap2_grad, B, N, H1,
+  ALT_DISPATCH(altcorr_bwd_kernel, 0, fmap1, fmap2, coords, corr_grad, fmap1_grad, fmap2_grad, B, N, H1,
                W1, H2, W2, C);
   B200_LAUNCH_OK("altcorr_bwd_kernel");
   return 0;
