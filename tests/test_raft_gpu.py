@@ -112,6 +112,62 @@ def test_lookup_vs_reference_golden(path):
     assert _maxabs(outd - z["out"]) <= 1e-4 * scale
 
 
+LOOKUP_CASES = [  # (B, H, W, levels, radius): level widths hit the 256-bit, 128-bit and scalar staging
+    (2, 16, 64, 4, 4), (1, 12, 40, 3, 3), (2, 9, 13, 2, 2), (1, 8, 24, 3, 1), (1, 20, 36, 2, 4), (1, 33, 32, 4, 4)]
+
+
+@pytest.mark.parametrize("case", LOOKUP_CASES, ids=[str(c) for c in LOOKUP_CASES])
+def test_lookup_shapes_vs_grid_sample(case):
+    """Every staging flavour of the lookup (row tails, misaligned level bases, integer / far /
+    non-finite coordinates) against F.grid_sample on the same device and the numpy oracle."""
+    from oracle import raft_oracle
+    from understanding_flow_robustness_b200 import coords_grid, raft_corr
+    B, H, W, L, r = case
+    torch.manual_seed(H * 100 + W)
+    pyr = [torch.randn(B * H * W, 1, H // 2 ** l, W // 2 ** l, device="cuda") for l in range(L)]
+    # one level lives at a 4-byte offset inside a bigger buffer: exercises the alignment dispatch
+    buf = torch.randn(pyr[-1].numel() + 1, device="cuda")
+    pyr[-1] = buf[1:].view_as(pyr[-1])
+    grid = coords_grid(B, H, W, "cuda")
+    for name, coords in [
+        ("integer", grid.clone()),                                   # round-trip noise around integers
+        ("near", grid + 2.5 * torch.randn(B, 2, H, W, device="cuda")),
+        ("far", grid + 60.0 * torch.randn(B, 2, H, W, device="cuda")),
+    ]:
+        out = raft_corr.lookup_forward(pyr, coords, r, H, W, "grid_sample")
+        c = coords.permute(0, 2, 3, 1)
+        outs = []
+        for i in range(L):
+            d = torch.linspace(-r, r, 2 * r + 1, device="cuda")
+            delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), axis=-1)
+            cl = c.reshape(B * H * W, 1, 1, 2) / 2 ** i + delta.view(1, 2 * r + 1, 2 * r + 1, 2)
+            Hl, Wl = pyr[i].shape[-2:]
+            xg, yg = cl.split([1, 1], dim=-1)
+            g = torch.cat([2 * xg / (Wl - 1) - 1, 2 * yg / (Hl - 1) - 1], dim=-1)
+            outs.append(F.grid_sample(pyr[i], g, align_corners=True).view(B, H, W, -1))
+        tref = torch.cat(outs, dim=-1).permute(0, 3, 1, 2).contiguous()
+        scale = float(tref.abs().max()) + 1e-6
+        # a level of extent 1 divides by zero in the reference's normalisation (NaN/inf there too)
+        ok = torch.isfinite(tref)
+        assert float((out - tref)[ok].abs().max()) <= 1e-5 * scale, name
+        assert bool((torch.isfinite(out) == ok).all()), name
+        ora = raft_oracle.lookup([p_.cpu().numpy() for p_ in pyr], coords.cpu().numpy(), r, unnorm="cuda")
+        okn = np.isfinite(ora)
+        assert _maxabs((out.cpu().numpy() - ora)[okn]) <= 2e-6 * scale, name
+    # non-finite coordinates must not fault; finite queries are unaffected
+    bad = grid + 2.5 * torch.randn(B, 2, H, W, device="cuda")
+    good = raft_corr.lookup_forward(pyr, bad, r, H, W, "direct")
+    bad2 = bad.clone()
+    bad2[0, 0, 0, 0] = float("nan")
+    bad2[0, 1, H - 1, W - 1] = float("inf")
+    bad2[0, 0, H // 2, W // 2] = 3e30
+    got = raft_corr.lookup_forward(pyr, bad2, r, H, W, "direct")
+    mask = torch.ones(B, 1, H, W, dtype=torch.bool, device="cuda")
+    mask[0, 0, 0, 0] = mask[0, 0, H - 1, W - 1] = mask[0, 0, H // 2, W // 2] = False
+    assert bool((got == good)[mask.expand_as(got)].all())
+    assert float(got[0, :, H // 2, W // 2].abs().max()) == 0.0
+
+
 TC_SHAPES = [(1, 32, 8, 32), (2, 64, 11, 20), (1, 40, 16, 36), (1, 256, 24, 64), (3, 8, 5, 8)]
 
 

@@ -5,10 +5,18 @@
 // the device, one F.grid_sample launch, then cat + permute + contiguous -- 4 grid_sample launches,
 // 4 H2D copies and 2 extra passes over the (B, 324, H, W) result per RAFT iteration.
 //
-// Here: ONE launch per lookup for all levels.  A CTA owns 32 consecutive query pixels of one level:
-//   phase 1: the (2r+4)^2 neighbourhood of every query is staged in shared memory (rows of the
-//            query's own H_l x W_l slice; zero outside the slice = grid_sample's zero padding);
-//   phase 2: warp = tap subset, lane = query, so every store of out[b, l*81 + k, q] is a full
+// Here: ONE launch per lookup for all levels.  A 4-warp CTA owns 32 consecutive query pixels of one
+// level; lane = query in every phase:
+//   staging: warp w fetches rows 3w..3w+2 of each query's (2r+4)^2 neighbourhood with sector-exact
+//            256-bit loads (level width % 8 == 0), 128-bit loads (width % 4 == 0) or scalar loads --
+//            only the rows and sectors the taps can touch, all of a warp's loads in flight together --
+//            and parks them UNSHIFTED in a query-minor shared tile win[row][column][query]: any
+//            per-query offset is bank-conflict free.  Everything outside the slice is staged as zero
+//            (= grid_sample's zero padding).  The gather costs one DRAM access per window row
+//            (scripts/probes/gather_probe.cu: ~53 G row accesses/s on a B200), so rows are trimmed,
+//            not bytes.
+//   taps:    the 2 x (2r+1) tap positions / fractions of every query are shared out over the warps;
+//   sample:  warp w takes the y offsets j = w, w+4, ...; every store of out[b, l*81 + k, q] is a full
 //            128-byte line; the result is written once, in its final (B, L*(2r+1)^2, H, W) layout.
 // Channel order k = i*(2r+1) + j with i the x offset and j the y offset (corr.py:80-86).
 //
@@ -35,6 +43,7 @@ struct LookupParams {
   const float *lvl[kMaxLevels];
   float *glvl[kMaxLevels];
   int LH[kMaxLevels], LW[kMaxLevels];
+  int path[kMaxLevels];  // forward staging flavour per level
   int num_levels, B, HW, radius, mode;
 };
 
@@ -112,118 +121,223 @@ __device__ __forceinline__ void build_taps(TapTables<R> &tt, const float *coords
   }
 }
 
-template <int R, bool VEC>
-__global__ void __launch_bounds__(256)
-lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float *__restrict__ out) {
-  constexpr int N = Geo<R>::N, WS = Geo<R>::WS;
-  constexpr int ROW = VEC ? Geo<R>::VROW : WS;
-  constexpr int QSTRIDE = VEC ? Geo<R>::VSTRIDE : Geo<R>::WSTRIDE;
-  __shared__ float win[QT * QSTRIDE];
-  __shared__ TapTables<R> tt;
-  const int lvl = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * QT;
-  const int LH = p.LH[lvl], LW = p.LW[lvl];
-  const float *vol = p.lvl[lvl];
+// 256-bit / 128-bit read-only loads that do not pollute L1 (every sector is used exactly once)
+__device__ __forceinline__ void ldg256(const float *p, float (&v)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ldg128(const float *p, float (&v)[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+               : "l"(p));
+}
 
-  build_taps<R>(tt, coords, b, q0, p.HW, lvl, LH, LW, p.mode);
-  __syncthreads();
+// grid_sample's accumulation nw*w + ne*w + sw*w + se*w with the contraction pinned, so that the
+// fast and the general sampling loop (and ATen's own FMA-contracted kernel) agree bit for bit
+__device__ __forceinline__ float bilerp(float c00, float c01, float c10, float c11, float ax, float bx,
+                                        float ay, float by) {
+  float v = __fmul_rn(c00, __fmul_rn(bx, by));
+  v = __fmaf_rn(c01, __fmul_rn(ax, by), v);
+  v = __fmaf_rn(c10, __fmul_rn(bx, ay), v);
+  return __fmaf_rn(c11, __fmul_rn(ax, ay), v);
+}
 
-  // phase 1: stage windows, thread = (query, window row)
-  for (int i = threadIdx.x; i < QT * WS; i += blockDim.x) {
-    const int qi = i / WS, r = i - qi * WS;
-    const int q = q0 + qi;
-    const int y = tt.oy[qi] + r, xo = tt.ox[qi];
-    const bool row_ok = q < p.HW && y >= 0 && y < LH;
-    if (VEC) {
-      float *dst = win + qi * QSTRIDE + r * ROW;
-      const int a0 = xo & ~3;  // aligned first column (floor to a multiple of 4, also for negatives)
-      const float4 *src = reinterpret_cast<const float4 *>(
-          vol + (((size_t)b * p.HW + (row_ok ? q : 0)) * LH + (row_ok ? y : 0)) * LW);
-      float v[Geo<R>::NV4 * 4];
+// one tap of one axis: position relative to the window origin `org` (or -1) and fraction
+template <int R>
+__device__ __forceinline__ void one_tap(float c, int lvl, int t, int size, int mode, int org, int &rel,
+                                        float &frac) {
+  constexpr int WS = 2 * R + 4;
+  const float x = sample_coord(c, lvl, t - R, size, mode);
+  const float fx = floorf(x);
+  if (fabsf(fx) < 1e8f) {
+    rel = (int)fx - org;
+    frac = x - fx;
+    // the round trip moves x by a few ulp at most: rel is within [0, WS-2]; clamp defensively
+    if (rel < 0 || rel > WS - 2) { rel = -1; frac = 0.f; }
+  } else {
+    rel = 0; frac = x - x;  // NaN propagates like in the reference
+  }
+}
+
+// Window origin floor(c / 2^l) - R - 1 from the un-rounded centre, and the window rows/columns
+// [lo, hi] the taps can touch: the coordinate arithmetic (fp32 add, and in grid_sample mode the
+// normalise / un-normalise round trip) moves a sample position by < 1e-3 pixel for |c| < 1024, so
+// unless the centre sits within 1/64 pixel of an integer, tap t lands exactly on window position
+// t + 1 and the outermost row/column on either side is never read.
+template <int R>
+__device__ __forceinline__ int window_origin(float c, int lvl, int &lo, int &hi) {
+  const float cl = c * (1.0f / (float)(1 << lvl));
+  float fo = floorf(cl);
+  const float f = cl - fo;
+  const bool interior = fabsf(cl) < 1024.f && f > 0.015625f && f < 0.984375f;
+  lo = interior ? 1 : 0;
+  hi = interior ? 2 * R + 2 : 2 * R + 3;
+  if (!(fabsf(fo) < 1e8f)) fo = -1e8f;  // non-finite / absurd coordinates: everything out of range
+  return (int)fo - R - 1;
+}
+
+constexpr int kCols = 16;  // staged columns per window row: (ox & 3) + 2r + 4 <= 15 for r <= 4
+enum { PATH_SCALAR = 0, PATH_VEC4 = 1, PATH_SECTOR = 2 };
+
+struct StageArgs {
+  const float *slice;  // this lane's H_l x W_l slice
+  int oy, ox, LH, LW;  // window origin, level extent
+  int ylo, yhi;        // window rows the taps touch
+  int clo, chi;        // staged columns the taps touch
+  bool q_ok;
+};
+
+// Stage window rows r0 .. r0+NR-1 (those below WS) of this lane's query: win[row][column][lane].
+// Staged column 0 is level column (ox & ~3) for the vector flavours, ox itself for the scalar one.
+// Only the rows and the 32-byte sectors the taps touch are fetched; everything outside the slice is
+// staged as zero (= grid_sample's zero padding).
+template <int PATH, int NR, int WS>
+__device__ __forceinline__ void stage_rows(float *win, int lane, const StageArgs &a, int r0) {
+  constexpr int NL = PATH == PATH_SECTOR ? 24 : PATH == PATH_VEC4 ? 16 : 12;   // loaded
+  constexpr int NC = PATH == PATH_SCALAR ? 12 : 16;                            // staged
+  float v[NR][NL];
+  // first loaded column: sector aligned / 16-byte aligned / exact
+  const int c0 = PATH == PATH_SECTOR ? (a.ox & ~7) : PATH == PATH_VEC4 ? (a.ox & ~3) : a.ox;
+  const bool hi4 = (a.ox & 4) != 0;  // PATH_SECTOR: staged column 0 is loaded column 4
+  // columns the taps touch, in loaded-column units
+  const int llo = PATH == PATH_SECTOR && hi4 ? a.clo + 4 : a.clo, lhi = PATH == PATH_SECTOR && hi4 ? a.chi + 4 : a.chi;
 #pragma unroll
-      for (int k = 0; k < Geo<R>::NV4; ++k) {
-        const int x = a0 + 4 * k;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row_ok && x >= 0 && x < LW) val = __ldg(src + (x >> 2));
-        v[4 * k] = val.x; v[4 * k + 1] = val.y; v[4 * k + 2] = val.z; v[4 * k + 3] = val.w;
+  for (int r = 0; r < NR; ++r) {
+    const int wr = r0 + r, y = a.oy + wr;
+    const bool row_ok = a.q_ok && wr >= a.ylo && wr <= a.yhi && y >= 0 && y < a.LH;
+    const float *src = a.slice + (size_t)(row_ok ? y : 0) * a.LW + c0;
+#pragma unroll
+    for (int k = 0; k < NL; ++k) v[r][k] = 0.f;
+    if (PATH == PATH_SECTOR) {
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {   // one 32-byte sector per load
+        const int x = c0 + 8 * g;
+        if (row_ok && x >= 0 && x < a.LW && lhi >= 8 * g && llo < 8 * g + 8)
+          ldg256(src + 8 * g, *reinterpret_cast<float(*)[8]>(&v[r][8 * g]));
       }
-      switch (xo & 3) {  // compile-time register indices inside each case
-        case 0:
+    } else if (PATH == PATH_VEC4) {
 #pragma unroll
-          for (int c = 0; c < WS; ++c) dst[c] = v[c];
-          break;
-        case 1:
-#pragma unroll
-          for (int c = 0; c < WS; ++c) dst[c] = v[c + 1];
-          break;
-        case 2:
-#pragma unroll
-          for (int c = 0; c < WS; ++c) dst[c] = v[c + 2];
-          break;
-        default:
-#pragma unroll
-          for (int c = 0; c < WS; ++c) dst[c] = v[c + 3];
-          break;
+      for (int g = 0; g < 4; ++g) {
+        const int x = c0 + 4 * g;
+        if (row_ok && x >= 0 && x < a.LW && lhi >= 4 * g && llo < 4 * g + 4)
+          ldg128(src + 4 * g, *reinterpret_cast<float(*)[4]>(&v[r][4 * g]));
       }
     } else {
-      float *dst = win + qi * QSTRIDE + r * ROW;
-      if (row_ok) {
-        const float *src = vol + (((size_t)b * p.HW + q) * LH + y) * LW;
 #pragma unroll
-        for (int c = 0; c < WS; ++c) {
-          const int x = xo + c;
-          dst[c] = (x >= 0 && x < LW) ? src[x] : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < WS; ++c) dst[c] = 0.f;
-      }
+      for (int k = 0; k < NL; ++k)
+        if (row_ok && c0 + k >= 0 && c0 + k < a.LW) v[r][k] = __ldg(src + k);
     }
   }
-  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    float *dst = win + ((r0 + r) * kCols) * 32 + lane;
+    if (r0 + r < WS) {
+#pragma unroll
+      for (int k = 0; k < NC; ++k) dst[k * 32] = (PATH == PATH_SECTOR) ? (hi4 ? v[r][k + 4] : v[r][k]) : v[r][k];
+    }
+  }
+}
 
-  // phase 2: lane = query, warp = y-offset row j; the x tap tables of the query live in registers
-  // and the two window rows are walked left to right, reusing the previous column pair whenever the
-  // next tap starts one pixel further (always, up to the reference's coordinate round-trip noise)
+// CTA = 4 warps x the same 32 queries of one level; lane = query everywhere.
+//   warp w stages window rows w*RPW .. and computes every 4th tap table entry   -> one barrier
+//   warp w samples the y offsets j = w, w+4, ...                                -> 128-byte stores
+template <int R>
+__global__ void __launch_bounds__(128, 4)
+lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float *__restrict__ out) {
+  constexpr int N = Geo<R>::N, WS = Geo<R>::WS, RPW = (WS + 3) / 4;
+  __shared__ float win[WS * kCols * 32];   // [row][column][lane]: conflict-free for any per-lane offset
+  __shared__ int tab_r[2 * N][32];         // tap tables [axis * N + tap][lane]
+  __shared__ float tab_a[2 * N][32];
+  // levels interleaved across consecutive CTAs: DRAM-heavy level 0 and the cache-resident coarse
+  // levels share every SM
+  const int lvl = blockIdx.x % p.num_levels, q0 = (blockIdx.x / p.num_levels) * QT, b = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = q0 + lane;
-  const float *w = win + lane * QSTRIDE;
-  const int nchan = p.num_levels * N * N;
+  const int mode = p.mode, path = p.path[lvl];
+  StageArgs a;
+  a.q_ok = q < p.HW;
+  a.LH = p.LH[lvl];
+  a.LW = p.LW[lvl];
+  float cx = 0.f, cy = 0.f;
+  if (a.q_ok) {
+    cx = coords[((size_t)b * 2 + 0) * p.HW + q];
+    cy = coords[((size_t)b * 2 + 1) * p.HW + q];
+  }
+  int xlo, xhi;
+  a.ox = window_origin<R>(cx, lvl, xlo, xhi);
+  a.oy = window_origin<R>(cy, lvl, a.ylo, a.yhi);
+  // staged column of window column 0, and the staged columns the taps touch
+  const int shift = path == PATH_SCALAR ? 0 : (a.ox & 3);
+  a.clo = shift + xlo; a.chi = shift + xhi;
+  a.slice = p.lvl[lvl] + ((size_t)b * p.HW + (a.q_ok ? q : 0)) * a.LH * a.LW;
+
+  // ---- stage this warp's rows (all of its loads are in flight together)
+  if (path == PATH_SECTOR) stage_rows<PATH_SECTOR, RPW, WS>(win, lane, a, warp * RPW);
+  else if (path == PATH_VEC4) stage_rows<PATH_VEC4, RPW, WS>(win, lane, a, warp * RPW);
+  else stage_rows<PATH_SCALAR, RPW, WS>(win, lane, a, warp * RPW);
+  // ---- this warp's share of the 2N tap table entries
+#pragma unroll 1
+  for (int e = warp; e < 2 * N; e += 4) {
+    const bool isy = e >= N;
+    int rel;
+    float frac;
+    one_tap<R>(isy ? cy : cx, lvl, isy ? e - N : e, isy ? a.LH : a.LW, mode, isy ? a.oy : a.ox, rel, frac);
+    // a tap outside the staged rows / columns cannot happen (window_origin); drop it if it does
+    const int lo = isy ? a.ylo : xlo, hi = isy ? a.yhi : xhi;
+    if (rel >= 0 && (rel < lo || rel + 1 > hi)) { rel = -1; frac = 0.f; }
+    tab_r[e][lane] = rel;
+    tab_a[e][lane] = frac;
+  }
+  __syncthreads();
+  if (!a.q_ok) return;
+
+  // ---- sample: every store is one full 128-byte line
   int rxs[N];
-  float axs[N];
+  float axs[N], bxs[N];
+  bool fast = true;   // x taps consecutive and inside the window (the common case)
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    rxs[i] = tt.x0[lane][i];
-    axs[i] = tt.ax[lane][i];
+    rxs[i] = tab_r[i][lane];
+    axs[i] = tab_a[i][lane];
+    bxs[i] = 1.f - axs[i];
+    fast = fast && rxs[i] == rxs[0] + i && rxs[0] >= 0;
   }
-  for (int j = warp; j < N; j += 8) {
-    const int ry = tt.y0[lane][j];
-    const float ay = tt.ay[lane][j], by = 1.f - ay;
-    const float *r0 = w + (ry >= 0 ? ry : 0) * ROW;
-    int prx = -100;
-    float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+  const int nchan = p.num_levels * N * N;
+  float *outq = out + ((size_t)b * nchan + (size_t)lvl * N * N) * p.HW + q;
+  const size_t istride = (size_t)N * p.HW;
+  const float *wl = win + lane;
+#pragma unroll 1
+  for (int j = warp; j < N; j += 4) {
+    const int ry = tab_r[N + j][lane];
+    const float ay = tab_a[N + j][lane], by = 1.f - ay;
+    float *o = outq + (size_t)j * p.HW;
+    if (fast && ry >= 0) {
+      // N+1 consecutive columns of both rows, then every tap is 4 products of registers
+      const float *r0 = wl + (ry * kCols + shift + rxs[0]) * 32;
+      float c0[N + 1], c1[N + 1];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const int rx = rxs[i];
-      float v = 0.f;
-      if (rx >= 0 && ry >= 0) {
-        if (rx == prx + 1) {
-          c00 = c01;
-          c10 = c11;
-        } else {
-          c00 = r0[rx];
-          c10 = r0[ROW + rx];
-        }
-        c01 = r0[rx + 1];
-        c11 = r0[ROW + rx + 1];
-        prx = rx;
-        // grid_sample: nw = (x1-x)(y1-y), ne = (x-x0)(y1-y), sw = (x1-x)(y-y0), se = (x-x0)(y-y0)
-        const float ax = axs[i], bx = 1.f - ax;
-        v = c00 * (bx * by);
-        v += c01 * (ax * by);
-        v += c10 * (bx * ay);
-        v += c11 * (ax * ay);
+      for (int k = 0; k <= N; ++k) {
+        c0[k] = r0[k * 32];
+        c1[k] = r0[(kCols + k) * 32];
       }
-      if (q < p.HW) out[((size_t)b * nchan + lvl * N * N + i * N + j) * p.HW + q] = v;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        *o = bilerp(c0[i], c0[i + 1], c1[i], c1[i + 1], axs[i], bxs[i], ay, by);
+        o += istride;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int rx = rxs[i];
+        float v = 0.f;
+        if (rx >= 0 && ry >= 0) {
+          const float *r0 = wl + (ry * kCols + shift + rx) * 32;
+          v = bilerp(r0[0], r0[32], r0[kCols * 32], r0[(kCols + 1) * 32], axs[i], bxs[i], ay, by);
+        }
+        *o = v;
+        o += istride;
+      }
     }
   }
 }
@@ -305,7 +419,7 @@ int fill_params(LookupParams &p, const float *const *lv, float *const *glv, int 
   p.num_levels = num_levels; p.B = B; p.HW = H * W; p.radius = radius; p.mode = mode;
   int h = H, w = W;
   for (int l = 0; l < kMaxLevels; ++l) {
-    p.lvl[l] = nullptr; p.glvl[l] = nullptr; p.LH[l] = 0; p.LW[l] = 0;
+    p.lvl[l] = nullptr; p.glvl[l] = nullptr; p.LH[l] = 0; p.LW[l] = 0; p.path[l] = 0;
     if (l < num_levels) {
       p.LH[l] = h; p.LW[l] = w;
       B200_CHECK(h >= 1 && w >= 1, "%s: pyramid level %d is empty (%dx%d input)", who, l, H, W);
@@ -328,19 +442,17 @@ int b200corr_lookup_forward(const float *const *h_levels, int num_levels, const 
   if (int e = fill_params(p, h_levels, nullptr, num_levels, B, H, W, radius, mode, "lookup_forward")) return e;
   if (B == 0) return 0;
   B200_CHECK(coords && out, "lookup_forward: null pointer");
-  dim3 grid((p.HW + QT - 1) / QT, num_levels, B);
-  bool vec = true;  // aligned float4 staging needs every level width % 4 == 0 and 16-byte aligned bases
-  for (int l = 0; l < num_levels; ++l) vec = vec && p.LW[l] % 4 == 0 && ((uintptr_t)p.lvl[l] & 15) == 0;
-#define LOOKUP_FWD(RR)                                                              \
-  if (vec) lookup_fwd_kernel<RR, true><<<grid, 256, 0, stream>>>(p, coords, out);   \
-  else lookup_fwd_kernel<RR, false><<<grid, 256, 0, stream>>>(p, coords, out)
-  switch (radius) {
-    case 1: LOOKUP_FWD(1); break;
-    case 2: LOOKUP_FWD(2); break;
-    case 3: LOOKUP_FWD(3); break;
-    default: LOOKUP_FWD(4); break;
+  for (int l = 0; l < num_levels; ++l) {
+    const uintptr_t a = (uintptr_t)p.lvl[l];
+    p.path[l] = (p.LW[l] % 8 == 0 && a % 32 == 0) ? PATH_SECTOR : (p.LW[l] % 4 == 0 && a % 16 == 0) ? PATH_VEC4 : PATH_SCALAR;
   }
-#undef LOOKUP_FWD
+  dim3 grid(((p.HW + QT - 1) / QT) * num_levels, 1, B);
+  switch (radius) {
+    case 1: lookup_fwd_kernel<1><<<grid, 128, 0, stream>>>(p, coords, out); break;
+    case 2: lookup_fwd_kernel<2><<<grid, 128, 0, stream>>>(p, coords, out); break;
+    case 3: lookup_fwd_kernel<3><<<grid, 128, 0, stream>>>(p, coords, out); break;
+    default: lookup_fwd_kernel<4><<<grid, 128, 0, stream>>>(p, coords, out); break;
+  }
   B200_LAUNCH_OK("lookup_fwd_kernel");
   return 0;
 }
