@@ -143,12 +143,30 @@ __device__ __forceinline__ float bilerp(float c00, float c01, float c10, float c
   return __fmaf_rn(c11, __fmul_rn(ax, ay), v);
 }
 
+// a / b correctly rounded from y = RN(1/b) (Markstein: q = RN(a*y), r = a - b*q exactly by FMA,
+// RN(q + r*y) is the correctly rounded quotient for every b whose significand is not all ones --
+// b is a small integer here).  Zero, non-finite and huge operands take the IEEE routine.
+__device__ __forceinline__ float div_by(float a, float b, float y) {
+  if (!(fabsf(a) < 1e30f) || !(b >= 1.f)) return __fdiv_rn(a, b);
+  const float q = __fmul_rn(a, y);
+  const float r = __fmaf_rn(-q, b, a);
+  return __fmaf_rn(r, y, q);
+}
+
+// sample_coord() with the reciprocal of (size - 1) hoisted: same value, a third of the instructions
+__device__ __forceinline__ float sample_coord_fast(float c, int lvl, int off, float sm1, float inv_sm1, int mode) {
+  const float x = __fadd_rn(__fmul_rn(c, 1.0f / (float)(1 << lvl)), (float)off);
+  if (mode == B200CORR_LOOKUP_DIRECT) return x;
+  const float g = __fsub_rn(div_by(__fmul_rn(2.0f, x), sm1, inv_sm1), 1.0f);
+  return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), sm1);   // x / 2 == x * 0.5 exactly
+}
+
 // one tap of one axis: position relative to the window origin `org` (or -1) and fraction
 template <int R>
-__device__ __forceinline__ void one_tap(float c, int lvl, int t, int size, int mode, int org, int &rel,
-                                        float &frac) {
+__device__ __forceinline__ void one_tap(float c, int lvl, int t, float sm1, float inv_sm1, int mode, int org,
+                                        int &rel, float &frac) {
   constexpr int WS = 2 * R + 4;
-  const float x = sample_coord(c, lvl, t - R, size, mode);
+  const float x = sample_coord_fast(c, lvl, t - R, sm1, inv_sm1, mode);
   const float fx = floorf(x);
   if (fabsf(fx) < 1e8f) {
     rel = (int)fx - org;
@@ -277,12 +295,14 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
   else if (path == PATH_VEC4) stage_rows<PATH_VEC4, RPW, WS>(win, lane, a, warp * RPW);
   else stage_rows<PATH_SCALAR, RPW, WS>(win, lane, a, warp * RPW);
   // ---- this warp's share of the 2N tap table entries
+  const float smx = (float)(a.LW - 1), smy = (float)(a.LH - 1);
+  const float ismx = __frcp_rn(smx), ismy = __frcp_rn(smy);
 #pragma unroll 1
   for (int e = warp; e < 2 * N; e += 4) {
     const bool isy = e >= N;
     int rel;
     float frac;
-    one_tap<R>(isy ? cy : cx, lvl, isy ? e - N : e, isy ? a.LH : a.LW, mode, isy ? a.oy : a.ox, rel, frac);
+    one_tap<R>(isy ? cy : cx, lvl, isy ? e - N : e, isy ? smy : smx, isy ? ismy : ismx, mode, isy ? a.oy : a.ox, rel, frac);
     // a tap outside the staged rows / columns cannot happen (window_origin); drop it if it does
     const int lo = isy ? a.ylo : xlo, hi = isy ? a.yhi : xhi;
     if (rel >= 0 && (rel < lo || rel + 1 > hi)) { rel = -1; frac = 0.f; }
