@@ -8,22 +8,32 @@
 // Here (precision TF32, the default):
 //   1. prep kernel: NCHW fp32 features -> [B][HW][Cp] (K-major) rounded to TF32 (cvt.rna), Cp = C
 //      rounded up to 32, zero padded.  7.9 MB/sample per map -- noise next to the volume.
-//   2. one persistent warp-specialised tcgen05 kernel.  CTA tile = 128 query pixels (M) x one 8x32
-//      spatial patch of key pixels (N = 256), K = Cp in blocks of 32 TF32 (128-byte swizzled rows).
-//        warp 0    : TMA producer (A: [Cp,HW,B] box 32x128; B: [Cp,W,H,B] box 32x32x8), 3-stage ring
-//        warp 1    : tcgen05.mma.kind::tf32 issuer (M128 N256 K8, 4 per k-block), accumulators in
-//                    TMEM, double buffered (2 x 256 columns)
+//   2. one persistent warp-specialised tcgen05 kernel run by CTA PAIRS (cluster of 2, cta_group::2).
+//      Pair tile = 256 query pixels (M, 128 per CTA) x one 8x32 spatial patch of key pixels (N = 256),
+//      K = Cp in blocks of 32 TF32 (128-byte swizzled rows).  Per CTA:
+//        warp 0    : TMA producer -- its own 128 query rows (A: [Cp,HW,B] box 32x128) and HALF of the
+//                    key patch (B: [Cp,W,H,B] box 32x32x4), 5-stage ring; the bytes of both CTAs are
+//                    counted on the leader's full barrier
+//        warp 1    : (leader CTA only) tcgen05.mma.cta_group::2.kind::tf32 issuer, M256 N256 K8, 4 per
+//                    k-block; accumulators in each CTA's TMEM, double buffered (2 x 256 columns);
+//                    commits are multicast to both CTAs' barriers
 //        warp 2    : TMEM allocator
-//        warps 4-11: two independent epilogue groups (4 warps each) that own alternate tiles / TMEM
-//                    buffers.  A thread owns one query row = the whole 8x32 patch of keys, read one
-//                    patch row (32 columns) at a time with tcgen05.ld, so the 2x2, 4x4 and 8x8
-//                    average pools are register-local.  Levels 0 and 1 go through a swizzled
-//                    per-warp staging tile and leave as full 128/64-byte lines (st.global.cs);
-//                    levels 2-3 are written straight from registers.
+//        warps 4-11: epilogue.  All 8 warps drain ONE accumulator at a time: warps 4-7 take patch rows
+//                    0-3, warps 8-11 patch rows 4-7 of the same 128 query rows; a thread owns one query
+//                    row, one patch row (32 columns) at a time with tcgen05.ld, so the 2x2 and 4x4
+//                    average pools are register-local and the 8x8 pool needs one 8-float hand-over
+//                    between the halves.  Levels 0 and 1 go through a swizzled per-warp staging tile
+//                    and leave as full 128/64-byte lines (st.global.cs); levels 2-3 are written
+//                    straight from registers.
 //      The volume is written exactly once and never re-read: 313 MB/sample instead of ~1.1 GB.
-//      Measured (profiles/): the kernel is bound by the L2 fabric -- 2.8 GB of
-//      operand re-reads at ~14 TB/s, then 1.25 GB of writes at HBM speed; a 2-CTA cluster with
-//      TMA multicast of the key patch was tried and does not reduce L2 traffic at cluster size 2.
+//      Measured (profiles/, DESIGN.md 2.3, scripts/ap_matrix.sh): MMAs alone 0.19 ms, + pooled
+//      levels 0.25 ms, + level 0 0.33 ms at B=4 -- the store-only pattern of this kernel runs at
+//      5.4 TB/s (scripts/probes/store_probe.cu), so the remaining gap is imperfect overlap: the
+//      operand reads of the MMAs, the TMA fills and the staging round trip of the epilogue share the
+//      shared-memory banks.  Tried and dropped: TMA stores for level 0 (32 scattered 128-byte rows per
+//      box: slower), 256-bit stores straight from registers (32 sectors per instruction: 1.8 TB/s),
+//      a cluster-scope release on the TMEM hand-over (puts a MEMBAR.GPU in front of every arrival).
+//      B200CORR_ALLPAIRS_CTAS=1 selects the single-CTA variant of the same kernel.
 //   Precision FP32 (exact, also the path for W % 4 != 0): a plain SIMT tile GEMM + pooling kernels.
 //
 // Error bound of the TF32 path (documented in DESIGN.md, asserted in tests): inputs are rounded to
@@ -63,19 +73,27 @@ prep_kmajor_tf32_kernel(const float *__restrict__ in, float *__restrict__ out, i
 namespace tc {
 constexpr int BM = 128, BN = 256, BK = 32;
 constexpr int PH = 8, PW = 32;  // key patch
-constexpr int NST = 4;
-constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_ROW_BYTES = 32 * 128;                 // one TMA store box: 32 query rows x 32 floats
-constexpr int EPI_WARP_BYTES = EPI_ROW_BYTES;           // per-warp staging tile: one patch row of 32 queries
+constexpr int EPI_ROW_BYTES = 32 * 128;                 // one staging tile: 32 query rows x 32 floats
 constexpr int EPI_WARPS = 8;
-constexpr int XBUF_BYTES = 0;
-constexpr int SMEM_BYTES = NST * STAGE_BYTES + EPI_WARPS * EPI_WARP_BYTES + XBUF_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int THREADS = 384;
 constexpr int TMEM_COLS = 512;
+// CTAS = 1: one CTA per 128 x 256 tile.  CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2)
+// per 256 x 256 tile -- each CTA stages its 128 query rows and HALF of the key patch (4 of the 8
+// patch rows), so a CTA pulls 256 KB instead of 384 KB of operands through the L2 per 128 x 256
+// outputs, and the smaller stages allow a deeper ring.
+template <int CTAS>
+struct Cfg {
+  static constexpr int NST = CTAS == 2 ? 5 : 3;
+  static constexpr int EPI_WARP_BYTES = EPI_ROW_BYTES;   // per-warp staging tile: one patch row of 32 queries
+  static constexpr int A_BYTES = BM * BK * 4, B_BYTES = (BN / CTAS) * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  // + level-2 rows handed from the upper-half to the lower-half epilogue warps (4 pairs x 2 slots x 1 KB)
+  static constexpr int XCH_BYTES = 4 * 2 * 1024;
+  static constexpr int SMEM_BYTES = NST * STAGE_BYTES + EPI_WARPS * EPI_WARP_BYTES + XCH_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+};
 
 struct Params {
   int B, HW, H, W, KB;       // KB = Cp / 32
-  int MT, NTY, NTX;          // tile counts
+  int MT, NTY, NTX;          // tile counts (MT counts 128*CTAS-row blocks)
   float scale;
   int debug;                 // B200CORR_DEBUG bits (diagnostics): 1 skip level-0 stores, 2 skip pooled stores
   float *lvl0;               // level 0
@@ -99,22 +117,30 @@ __device__ __forceinline__ void store_row_vec(float *dst, const float (&v)[N], i
   }
 }
 
+template <int CTAS>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const tc::Params p) {
   using namespace tc;
+  using C = Cfg<CTAS>;
+  constexpr int NST = C::NST, A_BYTES = C::A_BYTES, STAGE_BYTES = C::STAGE_BYTES, EPI_WARP_BYTES = C::EPI_WARP_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle atoms
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *sm = smem_raw + (base - raw);
   uint8_t *epi = sm + NST * STAGE_BYTES;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(epi + EPI_WARPS * EPI_WARP_BYTES + XBUF_BYTES);
+  float *xch = reinterpret_cast<float *>(epi + EPI_WARPS * EPI_WARP_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(epi + EPI_WARPS * EPI_WARP_BYTES + C::XCH_BYTES);
   uint64_t *full_bar = bars, *empty_bar = bars + NST;
   uint64_t *tfull_bar = bars + 2 * NST, *tempty_bar = bars + 2 * NST + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 4);
+  uint64_t *xfull_bar = bars + 2 * NST + 4, *xempty_bar = bars + 2 * NST + 12;   // [pair][slot]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA pair: rank 0 (the leader) owns the full / TMEM-empty barriers and issues the MMAs
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0;
+  const int unit = blockIdx.x / CTAS, nunits = gridDim.x / CTAS;   // tile scheduler granularity
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA);
@@ -125,16 +151,21 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);   // the 4 warps of the epilogue group that owns this buffer
+      mbar_init(&tempty_bar[s], EPI_WARPS * CTAS);   // every epilogue warp of every CTA reads every buffer
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&xfull_bar[s], 1);
+      mbar_init(&xempty_bar[s], 1);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_2cta(tmem_slot, TMEM_COLS); tmem_relinquish_2cta(); }
+    else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -142,28 +173,38 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const int total = p.B * p.MT * NT;
 
   if (warp == 0) {
-    // ================= TMA producer
+    // ================= TMA producer (every CTA: its own A rows and its share of the key patch)
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      uint32_t full_cluster[NST];   // CTAS == 2: the leader's full barriers, as cluster addresses
+      if (CTAS == 2)
+        for (int s = 0; s < NST; ++s) full_cluster[s] = map_to_cta(&full_bar[s], 0);
+      for (int t = unit; t < total; t += nunits) {
         const int nt = t % NT, mt = (t / NT) % p.MT, b = t / (NT * p.MT);
-        const int y0 = (nt / p.NTX) * PH, x0 = (nt % p.NTX) * PW, m0 = mt * BM;
+        const int y0 = (nt / p.NTX) * PH, x0 = (nt % p.NTX) * PW, m0 = (mt * CTAS + (int)rank) * BM;
         for (int kb = 0; kb < p.KB; ++kb, ++it) {
           const int st = it % NST;
           mbar_wait(&empty_bar[st], ((it / NST) & 1) ^ 1);
           uint8_t *a = sm + st * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[st], STAGE_BYTES);
-          tma_load_3d(a, &mapA, &full_bar[st], kb * BK, m0, b);
-          tma_load_4d(a + A_BYTES, &mapB, &full_bar[st], kb * BK, x0, y0, b);
+          if (CTAS == 2) {
+            // one arrival (the leader's) expects the bytes of both CTAs
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[st], 2 * STAGE_BYTES);
+            tma_load_3d_2cta(a, &mapA, full_cluster[st], kb * BK, m0, b);
+            tma_load_4d_2cta(a + A_BYTES, &mapB, full_cluster[st], kb * BK, x0, y0 + (int)rank * (PH / 2), b);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[st], STAGE_BYTES);
+            tma_load_3d(a, &mapA, &full_bar[st], kb * BK, m0, b);
+            tma_load_4d(a + A_BYTES, &mapB, &full_bar[st], kb * BK, x0, y0, b);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+    // ================= MMA issuer (single thread; of the leader CTA for a pair)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM * CTAS, BN);
       uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+      for (int t = unit; t < total; t += nunits, ++lt) {
         const int buf = lt & 1;
         mbar_wait(&tempty_bar[buf], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -176,30 +217,38 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           const uint64_t adesc = umma_desc_kmajor_sw128(a_addr);
           const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + A_BYTES);
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)  // 8 tf32 = 32 bytes per MMA: +2 in the 16-byte address field
-            umma_tf32(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
-          umma_commit(&empty_bar[st]);
+          for (int k4 = 0; k4 < 4; ++k4) {  // 8 tf32 = 32 bytes per MMA: +2 in the 16-byte address field
+            if (CTAS == 2) umma_tf32_2cta(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
+            else umma_tf32(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
+          }
+          if (CTAS == 2) umma_commit_2cta(&empty_bar[st]); else umma_commit(&empty_bar[st]);
         }
-        umma_commit(&tfull_bar[buf]);
+        if (CTAS == 2) umma_commit_2cta(&tfull_bar[buf]); else umma_commit(&tfull_bar[buf]);
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue: two independent groups of 4 warps.  Group g owns the tiles with
-    // local index lt % 2 == g, i.e. TMEM accumulator buffer g: while one group is storing its tile
-    // the other reads the next accumulator and the MMA warp fills the buffer after that.  (With a
-    // single group the three phases ran back to back: TMEM reads queue behind the MMAs in flight.)
-    // Warp w may only touch TMEM lanes 32*(w%4) .. +31; a thread owns one query row = the whole
-    // 8x32 key patch, one patch row (32 columns) at a time, so all average pools are register-local.
-    const int wq = warp & 3, grp = (warp - 4) >> 2;
+    // ================= epilogue: 8 warps drain ONE accumulator at a time.  Warp w may only touch TMEM
+    // lanes 32*(w%4) .. +31, so warps 4-7 (half 0) take patch rows 0-3 and warps 8-11 (half 1) patch
+    // rows 4-7 of the same 128 query rows.  A tile's stores then run at the SM's full store rate and
+    // the buffer goes back to the MMA warp after half the rows; the MMAs of the next tile run in the
+    // other buffer meanwhile.  (Two groups on alternate tiles each got half the store bandwidth and
+    // the MMA warp waited for TMEM: per-tile time (drain + mma) / 2 instead of max(drain, mma).)
+    // A thread owns one query row and 4 x 32 keys, one patch row (32 columns) at a time with
+    // tcgen05.ld, so the 2x2 and 4x4 average pools are register-local; the 8x8 pool needs the level-2
+    // row of the other half, handed from half 0 to half 1 through shared memory.
+    const int wq = warp & 3, half = (warp - 4) >> 2;
     uint8_t *ebuf = epi + (warp - 4) * EPI_WARP_BYTES;
     const bool m_dbg = !(p.debug & 2);
     const bool v1 = p.lvl[0] && (p.LW[0] % 4 == 0), v2 = p.lvl[1] && (p.LW[1] % 4 == 0),
                v3 = p.lvl[2] && (p.LW[2] % 4 == 0);
-    for (uint32_t lt = grp; (int)(blockIdx.x + lt * gridDim.x) < total; lt += 2) {
-      const int t = blockIdx.x + lt * gridDim.x;
+    const uint32_t tempty_leader[2] = {CTAS == 2 ? map_to_cta(&tempty_bar[0], 0) : 0u,
+                                       CTAS == 2 ? map_to_cta(&tempty_bar[1], 0) : 0u};
+    for (uint32_t lt = 0; (int)(unit + lt * nunits) < total; ++lt) {
+      const int t = unit + lt * nunits;
+      const int buf = lt & 1;
       const int nt = t % NT, mt = (t / NT) % p.MT, b = t / (NT * p.MT);
       const int y0 = (nt / p.NTX) * PH, x0 = (nt % p.NTX) * PW;
-      int mrow0 = mt * BM + wq * 32;
+      int mrow0 = (mt * CTAS + (int)rank) * BM + wq * 32;
       int m = mrow0 + lane;
       const bool m_ok = m < p.HW && m_dbg;
       size_t q = (size_t)b * p.HW + (m_ok ? m : 0);
@@ -209,25 +258,28 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         q = m;
       }
       const int bst = (p.debug & 4) ? 0 : b;
-      mbar_wait(&tfull_bar[grp], (lt >> 1) & 1);
+      mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + grp * BN + ((uint32_t)(wq * 32) << 16);
+      const uint32_t taddr = tmem_base + buf * BN + half * (PH / 2) * 32 + ((uint32_t)(wq * 32) << 16);
 
       // global pointers of this tile (coalesced write-out: lane -> (row, 16-byte chunk))
       float *vol0 = p.lvl0;
       const int wrow = lane >> 3, wchunk = lane & 7;      // level 0: 4 rows x 8 chunks per instruction
       const int xrow = lane >> 2, xchunk = lane & 3;      // level 1: 8 rows x 4 chunks per instruction
-      float prev[32], p1prev[16], p2prev[8];
+      float prev[32], p1prev[16];
 #pragma unroll
-      for (int r = 0; r < PH; ++r) {
+      for (int r = 0; r < PH / 2; ++r) {
+        const int pr = half * (PH / 2) + r;   // patch row
         float cur[32];
         tmem_ld_32x32(taddr + r * 32, cur);
         tmem_ld_wait();
-        if (r == PH - 1) {
-          // last TMEM read of this accumulator: hand the buffer back before the math / stores
+        if (r == PH / 2 - 1) {
+          // last TMEM read of this accumulator by this warp: hand it back before the math / stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+          if (lane == 0) {
+            if (CTAS == 2) mbar_arrive_cluster(tempty_leader[buf]); else mbar_arrive(&tempty_bar[buf]);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) cur[i] *= p.scale;
@@ -240,7 +292,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
         __syncwarp();
         if (!(p.debug & 1)) {
-          const int y = y0 + r, x = x0 + 4 * wchunk;
+          const int y = y0 + pr, x = x0 + 4 * wchunk;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int row = it * 4 + wrow;
@@ -257,7 +309,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           for (int j = 0; j < 16; ++j)
             p1[j] = (((prev[2 * j] + prev[2 * j + 1]) + cur[2 * j]) + cur[2 * j + 1]) * 0.25f;
           if (p.lvl[0] && m_dbg) {
-            const int y1 = y0 / 2 + (r >> 1), x1 = x0 / 2;
+            const int y1 = y0 / 2 + (pr >> 1), x1 = x0 / 2;
             if (v1) {
               // staged like level 0: [32 rows][64 B], chunk swizzled by (row >> 1) & 3
               __syncwarp();
@@ -278,30 +330,44 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
               store_row_vec(p.lvl[0] + (q * p.LH[0] + y1) * p.LW[0] + x1, p1, x1, p.LW[0], false);
             }
           }
-          if ((r & 3) == 3) {
+          if (r == PH / 2 - 1) {
             // ---- level 2: means of two level-1 rows -> 8 values
             float p2[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               p2[j] = (((p1prev[2 * j] + p1prev[2 * j + 1]) + p1[2 * j]) + p1[2 * j + 1]) * 0.25f;
             if (p.lvl[1] && m_ok) {
-              const int y2 = y0 / 4 + (r >> 2), x2 = x0 / 4;
+              const int y2 = y0 / 4 + half, x2 = x0 / 4;
               if (y2 < p.LH[1])
                 store_row_vec(p.lvl[1] + (q * p.LH[1] + y2) * p.LW[1] + x2, p2, x2, p.LW[1], v2);
             }
-            if (r == 7) {
-              float p3[4];
+            if (p.lvl[2]) {
+              // ---- level 3 = mean of the two level-2 rows of this patch: half 0 hands its row over
+              const int slot = wq * 2 + buf;
+              float *xs = xch + slot * 256 + lane;   // [value][lane]
+              if (half == 0) {
+                mbar_wait(&xempty_bar[slot], ((lt >> 1) & 1) ^ 1);
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                p3[j] = (((p2prev[2 * j] + p2prev[2 * j + 1]) + p2[2 * j]) + p2[2 * j + 1]) * 0.25f;
-              if (p.lvl[2] && m_ok) {
-                const int y3 = y0 / 8, x3 = x0 / 8;
-                if (y3 < p.LH[2])
-                  store_row_vec(p.lvl[2] + (q * p.LH[2] + y3) * p.LW[2] + x3, p3, x3, p.LW[2], v3);
+                for (int j = 0; j < 8; ++j) xs[j * 32] = p2[j];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xfull_bar[slot]);
+              } else {
+                mbar_wait(&xfull_bar[slot], (lt >> 1) & 1);
+                float p2prev[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) p2prev[j] = xs[j * 32];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xempty_bar[slot]);
+                float p3[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  p3[j] = (((p2prev[2 * j] + p2prev[2 * j + 1]) + p2[2 * j]) + p2[2 * j + 1]) * 0.25f;
+                if (m_ok) {
+                  const int y3 = y0 / 8, x3 = x0 / 8;
+                  if (y3 < p.LH[2])
+                    store_row_vec(p.lvl[2] + (q * p.LH[2] + y3) * p.LW[2] + x3, p3, x3, p.LW[2], v3);
+                }
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) p2prev[j] = p2[j];
             }
           } else {
 #pragma unroll
@@ -317,9 +383,10 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // nobody leaves while the peer can still signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTAS == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -427,6 +494,13 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
     B200_LAUNCH_OK("allpairs_simt_kernel");
   } else {
     const int Cp = (C + 31) / 32 * 32;
+    // CTA pairs (cta_group::2) by default; B200CORR_ALLPAIRS_CTAS=1 selects the single-CTA kernel
+    int ctas = 2;
+    {
+      const char *e = getenv("B200CORR_ALLPAIRS_CTAS");
+      if (e && atoi(e) == 1) ctas = 1;
+      if (b200::num_sms() % 2) ctas = 1;
+    }
     const size_t need = 2 * (size_t)B * HW * Cp * sizeof(float);
     B200_CHECK(workspace && workspace_bytes >= need,
                "allpairs_pyramid: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
@@ -451,14 +525,14 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
     {
       const uint64_t dims[4] = {(uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)B};
       const uint64_t str[4] = {4, (uint64_t)Cp * 4, (uint64_t)W * Cp * 4, (uint64_t)HW * Cp * 4};
-      const uint32_t box[4] = {tc::BK, tc::PW, tc::PH, 1};
+      const uint32_t box[4] = {tc::BK, tc::PW, (uint32_t)(tc::PH / ctas), 1};
       if (int e = b200::make_tensor_map(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, f2t, dims, str, box,
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
         return e;
     }
     tc::Params p;
     p.B = B; p.HW = HW; p.H = H; p.W = W; p.KB = Cp / 32;
-    p.MT = (HW + tc::BM - 1) / tc::BM;
+    p.MT = (HW + tc::BM * ctas - 1) / (tc::BM * ctas);
     p.NTY = (H + tc::PH - 1) / tc::PH;
     p.NTX = (W + tc::PW - 1) / tc::PW;
     p.scale = scale;
@@ -475,11 +549,28 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
       if (want) B200_CHECK(((uintptr_t)h_levels[l + 1] & 15) == 0, "allpairs_pyramid: level %d misaligned", l + 1);
     }
     first_unpooled = 4;
-    static bool attr_done[64] = {};  // per device
-    if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel, tc::SMEM_BYTES, attr_done)) return e;
     const int total = B * p.MT * p.NTY * p.NTX;
-    const int grid = total < b200::num_sms() ? total : b200::num_sms();
-    allpairs_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(mapA, mapB, p);
+    if (ctas == 2) {
+      static bool attr_done[64] = {};  // per device
+      if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel<2>, tc::Cfg<2>::SMEM_BYTES, attr_done)) return e;
+      const int pairs = b200::num_sms() / 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * (total < pairs ? total : pairs));
+      cfg.blockDim = dim3(tc::THREADS);
+      cfg.dynamicSmemBytes = tc::Cfg<2>::SMEM_BYTES;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      B200_CUDA(cudaLaunchKernelEx(&cfg, allpairs_tc_kernel<2>, mapA, mapB, p));
+    } else {
+      static bool attr_done[64] = {};  // per device
+      if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel<1>, tc::Cfg<1>::SMEM_BYTES, attr_done)) return e;
+      const int grid = total < b200::num_sms() ? total : b200::num_sms();
+      allpairs_tc_kernel<1><<<grid, tc::THREADS, tc::Cfg<1>::SMEM_BYTES, stream>>>(mapA, mapB, p);
+    }
     B200_LAUNCH_OK("allpairs_tc_kernel");
   }
   for (int l = first_unpooled; l < num_levels; ++l)
