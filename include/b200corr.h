@@ -49,6 +49,8 @@ extern "C" {
  * float/double/half on CUDA, correlation.cpp:104, correlation_cuda_kernel.cu:262) */
 #define B200CORR_F32 0
 #define B200CORR_F64 1
+#define B200CORR_F16 2   /* generic kernels only: half storage, fp32 arithmetic */
+#define B200CORR_BF16 3  /* generic kernels only: bfloat16 storage, fp32 arithmetic */
 
 /* precision of the all-pairs contraction */
 #define B200CORR_PREC_TF32 0   /* one tcgen05 kind::tf32 pass, inputs rounded to TF32 (rna)      */
@@ -162,6 +164,13 @@ int b200corr_altcorr_backward(const float *fmap1, const float *fmap2, const floa
 /* Runs `iters` dependent FP32 FMAs per thread on every SM and returns the achieved TFLOP/s in
  * *tflops (used by bench.py for the FP32-pipe roofline denominator). */
 int b200corr_measure_fp32_peak(int iters, float *tflops, void *stream);
+
+/* Window-gather ceiling of the memory system (the RAFT lookup's roofline; scripts/probes/gather_probe.cu):
+ * `nslices` contiguous slices of slice_bytes in buf (caller-provided, e.g. pyramid level 0), one
+ * 10-row x 64-byte window per slice at pitch_bytes per row, nothing else.  Returns 1e9 window rows
+ * per second in *grows_per_s. */
+int b200corr_measure_gather_peak(const float *buf, long long nslices, int slice_bytes, int pitch_bytes,
+                                 float *grows_per_s, void *stream);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t b200corr_launch_count(void);

@@ -154,6 +154,33 @@ def test_full_size_flownetc_properties():
     assert _rel(b.grad[5:6].cpu().numpy(), r2) <= 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+def test_half_precision_storage(dtype):
+    """The reference's CUDA dispatch accepts at::Half (correlation_cuda_kernel.cu:262,297).  Here fp16 /
+    bf16 tensors keep their type end to end, the arithmetic is fp32: the result must equal the fp32
+    operator applied to the same (already rounded) inputs up to ONE rounding to the storage type."""
+    from understanding_flow_robustness_b200 import spatial_correlation_sample
+    torch.manual_seed(5)
+    kw = dict(kernel_size=1, patch_size=21, stride=1, padding=0, dilation=1, dilation_patch=2)
+    for shape, kw_ in [((2, 32, 12, 20), kw), ((1, 6, 9, 10), dict(kernel_size=3, patch_size=3, stride=2, padding=1, dilation=1, dilation_patch=2))]:
+        a = torch.randn(*shape, device="cuda").to(dtype).requires_grad_()
+        b = torch.randn(*shape, device="cuda").to(dtype).requires_grad_()
+        out = spatial_correlation_sample(a, b, **kw_)
+        assert out.dtype == dtype
+        g = torch.randn(out.shape, device="cuda").to(dtype)
+        out.backward(g)
+        a32 = a.detach().float().requires_grad_()
+        b32 = b.detach().float().requires_grad_()
+        ref = spatial_correlation_sample(a32, b32, **kw_)
+        ref.backward(g.float())
+        # one rounding to the storage type (fp16: 2^-11, bf16: 2^-8 relative) on top of fp32 arithmetic
+        eps = 2.0 ** -11 if dtype == torch.float16 else 2.0 ** -8
+        for got, want in ((out.detach(), ref.detach()), (a.grad, a32.grad), (b.grad, b32.grad)):
+            assert got.dtype == dtype
+            err = (got.float() - want).abs()
+            assert bool((err <= 1.01 * eps * want.abs() + 1e-5 * float(want.abs().max())).all()), float(err.max())
+
+
 def test_gradcheck_fp64():
     """grad_check.py:9-55 equivalent."""
     from understanding_flow_robustness_b200 import SpatialCorrelationSampler

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "b200corr_altcorr_forward": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
     "b200corr_altcorr_backward": (c_int, [c_void_p] * 7 + [c_int] * 8 + [c_void_p]),
     "b200corr_measure_fp32_peak": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p]),
+    "b200corr_measure_gather_peak": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, ctypes.POINTER(c_float), c_void_p]),
     "b200corr_launch_count": (ctypes.c_uint64, []),
     "b200corr_probe_lds": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float), c_void_p]),
     "b200corr_probe_ffma_toeplitz": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p]),

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-_DTYPES = {torch.float32: 0, torch.float64: 1}
+_DTYPES = {torch.float32: 0, torch.float64: 1, torch.float16: 2, torch.bfloat16: 3}
 
 
 def _check_inputs(who, *tensors):
@@ -29,7 +29,7 @@ def _check_inputs(who, *tensors):
         if t.dtype != first.dtype:
             raise RuntimeError(f"{who}: inputs must have the same dtype")
     if first.dtype not in _DTYPES:
-        raise RuntimeError(f"{who}: unsupported dtype {first.dtype} (float32 / float64)")
+        raise RuntimeError(f"{who}: unsupported dtype {first.dtype} (float32 / float64 / float16 / bfloat16)")
     return _DTYPES[first.dtype]
 
 

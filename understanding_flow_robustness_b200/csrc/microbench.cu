@@ -118,6 +118,41 @@ __global__ void __launch_bounds__(256, 1) ffma_toeplitz_kernel(float *sink, int 
 
 }  // namespace
 
+// ---- window-gather ceiling: every thread owns a contiguous slice of `slice_sectors` 32-byte sectors
+// (one RAFT query's H_l x W_l volume slice) and reads a window of `rows` rows x 2 sectors at a random
+// position inside it, row pitch `pitch_sectors` -- the access pattern of the correlation lookup with
+// nothing else attached (all loads in flight at once, 2048 threads per SM).
+template <int ROWS>
+__global__ void __launch_bounds__(256)
+gather_probe_kernel(const float *__restrict__ buf, size_t nslices, int slice_sectors, int pitch_sectors,
+                    float *sink) {
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  uint32_t h = (uint32_t)tid;
+  h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+  const int rows_avail = slice_sectors / pitch_sectors - ROWS;
+  const size_t base = (tid % nslices) * slice_sectors + (h % (uint32_t)rows_avail) * pitch_sectors +
+                      ((h >> 8) % (uint32_t)(pitch_sectors - 1));
+  float v[ROWS][2][8];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float *p = buf + (base + (size_t)r * pitch_sectors + k) * 8;
+      asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(v[r][k][0]), "=f"(v[r][k][1]), "=f"(v[r][k][2]), "=f"(v[r][k][3]), "=f"(v[r][k][4]),
+                     "=f"(v[r][k][5]), "=f"(v[r][k][6]), "=f"(v[r][k][7])
+                   : "l"(p));
+    }
+  float acc = 0.f;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[r][k][j];
+  if (acc == 123.456f) sink[0] = acc;
+}
+
 extern "C" {
 
 // cycles per LDS.128 warp-instruction per SM at `warps` resident warps (one CTA per SM).
@@ -199,6 +234,42 @@ int b200corr_probe_ffma_toeplitz(int iters, float *tflops, void *stream_) {
   }
   B200_LAUNCH_OK("ffma_toeplitz_kernel");
   *tflops = (float)(2.0 * 168 * (double)iters * blocks * 256 / (best * 1e-3) / 1e12);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return 0;
+}
+
+// window rows gathered per second (in units of 1e9) when nothing but the gather runs: `nslices`
+// slices of slice_bytes each (buffer provided by the caller, >= nslices * slice_bytes, 32-B aligned),
+// one 10-row x 64-byte window per slice and launch, row pitch pitch_bytes
+int b200corr_measure_gather_peak(const float *buf, long long nslices, int slice_bytes, int pitch_bytes,
+                                 float *grows_per_s, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK(buf && grows_per_s && nslices >= 256 && slice_bytes % 32 == 0 && pitch_bytes % 32 == 0 &&
+                 pitch_bytes >= 64 && slice_bytes / pitch_bytes > 10 && ((uintptr_t)buf & 31) == 0,
+             "measure_gather_peak: bad arguments");
+  float *sink = nullptr;
+  B200_CUDA(cudaMalloc(&sink, sizeof(float)));
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0));
+  B200_CUDA(cudaEventCreate(&e1));
+  // 8 windows per slice and launch so that a launch lasts long enough to time
+  const long long threads = nslices * 8;
+  const int blocks = (int)((threads + 255) / 256);
+  gather_probe_kernel<10><<<blocks, 256, 0, stream>>>(buf, (size_t)nslices, slice_bytes / 32, pitch_bytes / 32, sink);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    B200_CUDA(cudaEventRecord(e0, stream));
+    gather_probe_kernel<10><<<blocks, 256, 0, stream>>>(buf, (size_t)nslices, slice_bytes / 32, pitch_bytes / 32, sink);
+    B200_CUDA(cudaEventRecord(e1, stream));
+    B200_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  B200_LAUNCH_OK("gather_probe_kernel");
+  *grows_per_s = (float)((double)blocks * 256 * 10 / (best * 1e-3) / 1e9);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(sink);

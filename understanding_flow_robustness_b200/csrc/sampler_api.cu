@@ -13,7 +13,7 @@ namespace {
 
 int check_common(const char *who, int B, int C, int H, int W, const int *q, int dtype, int *oH,
                  int *oW) {
-  B200_CHECK(dtype == B200CORR_F32 || dtype == B200CORR_F64, "%s: unsupported dtype %d", who, dtype);
+  B200_CHECK(dtype >= B200CORR_F32 && dtype <= B200CORR_BF16, "%s: unsupported dtype %d", who, dtype);
   B200_CHECK(B >= 0 && C >= 0 && H >= 0 && W >= 0, "%s: negative tensor size", who);
   B200_CHECK(q[0] >= 1 && q[1] >= 1 && q[2] >= 1 && q[3] >= 1, "%s: kernel/patch size must be >= 1",
              who);

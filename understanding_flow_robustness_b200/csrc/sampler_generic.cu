@@ -1,4 +1,5 @@
-// sampler_generic.cu -- spatial correlation sampler for ARBITRARY hyper-parameters and fp32/fp64.
+// sampler_generic.cu -- spatial correlation sampler for ARBITRARY hyper-parameters and fp32 / fp64 /
+// fp16 / bf16 storage.
 //
 // Replaces the role of correlation_cuda_kernel.cu:22-233 (reference CUDA kernels) for every
 // configuration the register-blocked TMA kernels in sampler_fast.cu do not cover (kernel_size > 1,
@@ -10,6 +11,13 @@
 // Products and sums use __fmul_rn/__fadd_rn (no FMA contraction), so on identical inputs the result
 // is bit-identical to the reference's CPU build -- the -m gpu tests assert equality, and the fast
 // kernels are checked against these at full problem sizes.
+// Half precision (the reference's CUDA dispatch accepts at::Half, correlation_cuda_kernel.cu:262,297;
+// its CPU dispatch does not): fp16 / bf16 tensors are read and written in their own type, products
+// and sums are carried in fp32 and rounded once on the final store -- at least as accurate as the
+// reference, which accumulates in half.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -18,6 +26,23 @@ struct SamplerParams {
   int B, C, H, W, oH, oW;
   int kH, kW, patchH, patchW, padH, padW, dilH, dilW, dpH, dpW, sH, sW;
 };
+
+// storage type -> arithmetic type
+template <typename T> struct Acc { using type = T; };
+template <> struct Acc<__half> { using type = float; };
+template <> struct Acc<__nv_bfloat16> { using type = float; };
+template <typename T>
+__device__ __forceinline__ typename Acc<T>::type ld(const T *p) { return *p; }
+template <>
+__device__ __forceinline__ float ld<__half>(const __half *p) { return __half2float(*p); }
+template <>
+__device__ __forceinline__ float ld<__nv_bfloat16>(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ void st(T *p, typename Acc<T>::type v) { *p = v; }
+template <>
+__device__ __forceinline__ void st<__half>(__half *p, float v) { *p = __float2half_rn(v); }
+template <>
+__device__ __forceinline__ void st<__nv_bfloat16>(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
 template <typename T>
 __device__ __forceinline__ T mul_rn(T a, T b);
@@ -52,7 +77,8 @@ sampler_generic_forward_kernel(const T *__restrict__ in1, const T *__restrict__ 
     const int u = -p.padH + h * p.sH, v = -p.padW + w * p.sW;
     const T *a = in1 + (size_t)n * p.C * p.H * p.W;
     const T *b = in2 + (size_t)n * p.C * p.H * p.W;
-    T acc = T(0);
+    using A = typename Acc<T>::type;
+    A acc = A(0);
     for (int c = 0; c < p.C; ++c) {
       for (int i = 0; i < p.kH; ++i) {
         int i1 = u + i * p.dilH, i2 = i1 + shiftU;
@@ -60,13 +86,13 @@ sampler_generic_forward_kernel(const T *__restrict__ in1, const T *__restrict__ 
         for (int j = 0; j < p.kW; ++j) {
           int j1 = v + j * p.dilW, j2 = j1 + shiftV;
           if (j1 < 0 || j1 >= p.W || j2 < 0 || j2 >= p.W) continue;
-          acc = add_rn(acc, mul_rn(a[(size_t)i1 * p.W + j1], b[(size_t)i2 * p.W + j2]));
+          acc = add_rn(acc, mul_rn(ld(a + (size_t)i1 * p.W + j1), ld(b + (size_t)i2 * p.W + j2)));
         }
       }
       a += (size_t)p.H * p.W;
       b += (size_t)p.H * p.W;
     }
-    out[idx] = acc;
+    st(out + idx, acc);
   }
 }
 
@@ -84,8 +110,9 @@ sampler_generic_backward_kernel(const T *__restrict__ other, const T *__restrict
     t /= p.H;
     int c = (int)(t % p.C);
     int n = (int)(t / p.C);
+    using A = typename Acc<T>::type;
     const T *oth = other + ((size_t)n * p.C + c) * p.H * p.W;
-    T acc = T(0);
+    A acc = A(0);
     for (int ph = 0; ph < p.patchH; ++ph) {
       const int dy = (ph - (p.patchH - 1) / 2) * p.dpH;
       const int y1 = (WHICH == 1) ? y : y - dy;  // tap position in input1
@@ -96,7 +123,7 @@ sampler_generic_backward_kernel(const T *__restrict__ other, const T *__restrict
         const int x1 = (WHICH == 1) ? x : x - dx;
         const int x2 = x1 + dx;
         if (x1 < 0 || x1 >= p.W || x2 < 0 || x2 >= p.W) continue;
-        const T ov = (WHICH == 1) ? oth[(size_t)y2 * p.W + x2] : oth[(size_t)y1 * p.W + x1];
+        const A ov = (WHICH == 1) ? ld(oth + (size_t)y2 * p.W + x2) : ld(oth + (size_t)y1 * p.W + x1);
         const T *g = gout + (((size_t)n * p.patchH + ph) * p.patchW + pw) * p.oH * p.oW;
         // y1 = h*sH - padH + i*dilH ; i descending <=> h ascending (reference visiting order)
         for (int i = p.kH - 1; i >= 0; --i) {
@@ -109,12 +136,12 @@ sampler_generic_backward_kernel(const T *__restrict__ other, const T *__restrict
             if (wn < 0 || wn % p.sW) continue;
             int w = wn / p.sW;
             if (w >= p.oW) continue;
-            acc = add_rn(acc, mul_rn(g[(size_t)h * p.oW + w], ov));
+            acc = add_rn(acc, mul_rn(ld(g + (size_t)h * p.oW + w), ov));
           }
         }
       }
     }
-    gin[idx] = acc;
+    st(gin + idx, acc);
   }
 }
 
@@ -157,8 +184,12 @@ int sampler_generic_forward(const void *in1, const void *in2, void *out, int B, 
                             int oH, int oW, const int *q, int dtype, cudaStream_t stream) {
   SamplerParams p{B, C, H, W, oH, oW, q[0], q[1], q[2], q[3], q[4], q[5],
                   q[6], q[7], q[8], q[9], q[10], q[11]};
-  return dtype == B200CORR_F64 ? launch_forward<double>(in1, in2, out, p, stream)
-                               : launch_forward<float>(in1, in2, out, p, stream);
+  switch (dtype) {
+    case B200CORR_F64: return launch_forward<double>(in1, in2, out, p, stream);
+    case B200CORR_F16: return launch_forward<__half>(in1, in2, out, p, stream);
+    case B200CORR_BF16: return launch_forward<__nv_bfloat16>(in1, in2, out, p, stream);
+    default: return launch_forward<float>(in1, in2, out, p, stream);
+  }
 }
 
 int sampler_generic_backward(const void *in1, const void *in2, const void *gout, void *gin1,
@@ -166,8 +197,12 @@ int sampler_generic_backward(const void *in1, const void *in2, const void *gout,
                              int dtype, cudaStream_t stream) {
   SamplerParams p{B, C, H, W, oH, oW, q[0], q[1], q[2], q[3], q[4], q[5],
                   q[6], q[7], q[8], q[9], q[10], q[11]};
-  return dtype == B200CORR_F64 ? launch_backward<double>(in1, in2, gout, gin1, gin2, p, stream)
-                               : launch_backward<float>(in1, in2, gout, gin1, gin2, p, stream);
+  switch (dtype) {
+    case B200CORR_F64: return launch_backward<double>(in1, in2, gout, gin1, gin2, p, stream);
+    case B200CORR_F16: return launch_backward<__half>(in1, in2, gout, gin1, gin2, p, stream);
+    case B200CORR_BF16: return launch_backward<__nv_bfloat16>(in1, in2, gout, gin1, gin2, p, stream);
+    default: return launch_backward<float>(in1, in2, gout, gin1, gin2, p, stream);
+  }
 }
 
 }  // namespace b200
