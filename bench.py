@@ -167,7 +167,7 @@ def run_reference_arm(args):
             "data": "synthetic", "config": workload_config(args.gpus), "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def workload_config(n):
@@ -180,7 +180,27 @@ def workload_config(n):
 
 
 # ---------------------------------------------------------------------------- GPU arm
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Libraries print to fd 1 (NCCL's version banner, torchrun children): keep the real stdout for the
+    one JSON line and send everything else to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -356,7 +376,7 @@ def main():
         except Exception as e:  # never lose the GPU numbers to a host-side problem
             line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "unavailable",
                                     "sample": f"{type(e).__name__}: {e}"}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

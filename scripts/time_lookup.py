@@ -27,3 +27,36 @@ for mode in ("grid_sample", "direct"):
     ms = e0.elapsed_time(e1) / 60
     gb = B * 7680 * (324 * 4 + 4 * 100 * 4) / 1e9
     print(f"lookup {mode}: {ms * 1e3:.1f} us  ({gb / ms * 1e3:.0f} GB/s algorithmic)")
+
+# ---- backward: 12 lookups accumulate into one gradient pyramid, then pyramid fold + two bmm
+from understanding_flow_robustness_b200 import CorrBlock
+
+f1g = f1.clone().requires_grad_()
+f2g = f2.clone().requires_grad_()
+def fwd_bwd(parts):
+    blk = CorrBlock(f1g, f2g, 4, 4)
+    outs = [blk(c) for c in cs]
+    loss = sum(o.sum() for o in outs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss.backward()
+    e1.record()
+    torch.cuda.synchronize()
+    f1g.grad = f2g.grad = None
+    return e0.elapsed_time(e1)
+fwd_bwd(0)
+ts = [fwd_bwd(0) for _ in range(3)]
+print(f"CorrBlock backward (12 lookups + pyramid fold + 2 bmm, B={B}): {min(ts):.3f} ms")
+g = torch.randn_like(o)
+glv = [torch.zeros_like(v) for v in pyr]
+for _ in range(2):
+    raft_corr.lookup_backward(glv, cs[0], g, 4, 48, 160, "grid_sample")
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for c in cs:
+    raft_corr.lookup_backward(glv, c, g, 4, 48, 160, "grid_sample")
+e1.record()
+torch.cuda.synchronize()
+print(f"lookup backward: {e0.elapsed_time(e1) / 12 * 1e3:.1f} us per lookup")

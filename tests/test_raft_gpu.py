@@ -154,6 +154,28 @@ def test_lookup_shapes_vs_grid_sample(case):
         ora = raft_oracle.lookup([p_.cpu().numpy() for p_ in pyr], coords.cpu().numpy(), r, unnorm="cuda")
         okn = np.isfinite(ora)
         assert _maxabs((out.cpu().numpy() - ora)[okn]) <= 2e-6 * scale, name
+        # backward: gradient w.r.t. every pyramid level vs autograd through grid_sample; two calls
+        # accumulate into the same gradient pyramid (what 12 RAFT iterations do)
+        if bool(ok.all()):
+            gout = torch.randn_like(out)
+            leaves = [p_.detach().clone().requires_grad_() for p_ in pyr]
+            outs = []
+            for i in range(L):
+                d = torch.linspace(-r, r, 2 * r + 1, device="cuda")
+                delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), axis=-1)
+                cl = c.reshape(B * H * W, 1, 1, 2) / 2 ** i + delta.view(1, 2 * r + 1, 2 * r + 1, 2)
+                Hl, Wl = leaves[i].shape[-2:]
+                xg, yg = cl.split([1, 1], dim=-1)
+                g = torch.cat([2 * xg / (Wl - 1) - 1, 2 * yg / (Hl - 1) - 1], dim=-1)
+                outs.append(F.grid_sample(leaves[i], g, align_corners=True).view(B, H, W, -1))
+            (torch.cat(outs, dim=-1).permute(0, 3, 1, 2) * gout).sum().backward()
+            glv = [torch.zeros_like(p_) for p_ in pyr]
+            glv[-1] = torch.zeros(pyr[-1].numel() + 1, device="cuda")[1:].view_as(pyr[-1])   # misaligned level
+            raft_corr.lookup_backward(glv, coords, gout, r, H, W, "grid_sample")
+            raft_corr.lookup_backward(glv, coords, gout, r, H, W, "grid_sample")
+            for i in range(L):
+                want = 2 * leaves[i].grad
+                assert float((glv[i] - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-6, (name, i)
     # non-finite coordinates must not fault; finite queries are unaffected
     bad = grid + 2.5 * torch.randn(B, 2, H, W, device="cuda")
     good = raft_corr.lookup_forward(pyr, bad, r, H, W, "direct")
@@ -227,6 +249,28 @@ def test_corrblock_end_to_end_and_autograd():
         blk2 = CorrBlock(f1, f2, num_levels=L, radius=r, precision="fp32")
         assert [tuple(v.shape) for v in blk2.get_corr_pyramid()] == [(B * H * W, 1, H // 2 ** l, W // 2 ** l) for l in range(L)]
         assert float((blk2(ca) - oa).abs().max()) == 0.0
+
+
+def test_corrblock_tf32_gradients():
+    """precision="tf32": volume and both gradient GEMMs on the tensor cores; against the exact path
+    the gradients stay within the TF32 input-rounding bound (relative 2^-10 per product)."""
+    from understanding_flow_robustness_b200 import CorrBlock, coords_grid
+    torch.manual_seed(11)
+    B, C, H, W, L, r = 1, 64, 16, 32, 3, 3
+    f1 = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+    f2 = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+    c = coords_grid(B, H, W, "cuda") + 2.0 * torch.randn(B, 2, H, W, device="cuda")
+    grads = {}
+    for prec in ("fp32", "tf32"):
+        f1.grad = f2.grad = None
+        blk = CorrBlock(f1, f2, num_levels=L, radius=r, precision=prec)
+        out = blk(c)
+        torch.manual_seed(12)
+        (out * torch.randn_like(out)).sum().backward()
+        grads[prec] = (f1.grad.clone(), f2.grad.clone())
+    for a, b in zip(grads["tf32"], grads["fp32"]):
+        assert float((a - b).abs().max()) <= 4e-3 * float(b.abs().max())
+        assert float((a - b).abs().max()) > 0.0   # the TF32 path really ran
 
 
 @pytest.mark.parametrize("path", RAFT[:2], ids=[os.path.basename(p)[:-4] for p in RAFT[:2]])

@@ -72,55 +72,6 @@ struct Geo {
   static constexpr int VSTRIDE = (WS * VROW) | 1;
 };
 
-// per-query per-axis tap tables in shared memory
-template <int R>
-struct TapTables {
-  int x0[QT][Geo<R>::N];   // floor of the sample coordinate, relative to the window origin
-  float ax[QT][Geo<R>::N]; // fractional part
-  int y0[QT][Geo<R>::N];
-  float ay[QT][Geo<R>::N];
-  int ox[QT], oy[QT];      // window origin in the level's pixel coordinates
-};
-
-template <int R>
-__device__ __forceinline__ void build_taps(TapTables<R> &tt, const float *coords, int b, int q0,
-                                           int HW, int lvl, int LH, int LW, int mode) {
-  constexpr int N = Geo<R>::N;
-  // one task per (query, axis, tap): 32 * 2 * N tasks spread over the whole CTA (the two IEEE
-  // divisions of the grid_sample round trip make a tap ~80 instructions)
-  for (int i = threadIdx.x; i < QT * 2 * N; i += blockDim.x) {
-    const int t = i % N;
-    const int qa = i / N;
-    const int qi = qa >> 1, axis = qa & 1;
-    const int q = q0 + qi;
-    float c = 0.f;
-    if (q < HW) c = coords[((size_t)b * 2 + axis) * HW + q];
-    const int size = axis == 0 ? LW : LH;
-    // window origin from the un-rounded centre: floor(c / 2^l) - R - 1
-    const float cl = c * (1.0f / (float)(1 << lvl));
-    float fo = floorf(cl);
-    if (!(fabsf(fo) < 1e8f)) fo = -1e8f;  // non-finite / absurd coordinates: everything out of range
-    const int org = (int)fo - R - 1;
-    if (t == 0) {
-      if (axis == 0) tt.ox[qi] = org; else tt.oy[qi] = org;
-    }
-    const float x = sample_coord(c, lvl, t - R, size, mode);
-    float fx = floorf(x);
-    int rel;
-    float frac;
-    if (fabsf(fx) < 1e8f) {
-      rel = (int)fx - org;
-      frac = x - fx;
-      // the round trip moves x by a few ulp at most: rel is within [0, WS-2]; clamp defensively
-      if (rel < 0 || rel > Geo<R>::WS - 2) { rel = -1; frac = 0.f; }
-    } else {
-      rel = 0; frac = x - x;  // NaN propagates like in the reference
-    }
-    if (axis == 0) { tt.x0[qi][t] = rel; tt.ax[qi][t] = frac; }
-    else           { tt.y0[qi][t] = rel; tt.ay[qi][t] = frac; }
-  }
-}
-
 // 256-bit / 128-bit read-only loads that do not pollute L1 (every sector is used exactly once)
 __device__ __forceinline__ void ldg256(const float *p, float (&v)[8]) {
   asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -362,55 +313,195 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
   }
 }
 
-template <int R>
-__global__ void __launch_bounds__(256)
-lookup_bwd_kernel(const LookupParams p, const float *__restrict__ coords,
-                  const float *__restrict__ gout) {
-  constexpr int N = Geo<R>::N, WS = Geo<R>::WS, WSTRIDE = Geo<R>::WSTRIDE;
-  __shared__ float win[QT * WSTRIDE];
-  __shared__ TapTables<R> tt;
-  const int lvl = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * QT;
-  const int LH = p.LH[lvl], LW = p.LW[lvl];
-  float *gvol = p.glvl[lvl];
+// plain (coherent) 256-bit / 128-bit accesses for the read-modify-write of the gradient slices
+__device__ __forceinline__ void ld256(const float *p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void st256(float *p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
 
-  build_taps<R>(tt, coords, b, q0, p.HW, lvl, LH, LW, p.mode);
-  for (int i = threadIdx.x; i < QT * WSTRIDE; i += blockDim.x) win[i] = 0.f;
-  __syncthreads();
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q = q0 + lane;
-  float *w = win + lane * WSTRIDE;
-  const int nchan = p.num_levels * N * N;
-  // lane = query: two taps of the same query are handled by different warps -> shared atomics
-  for (int k = warp; k < N * N; k += 8) {
-    const int i = k / N, j = k - i * N;
-    const int rx = tt.x0[lane][i], ry = tt.y0[lane][j];
-    if (q < p.HW && rx >= 0 && ry >= 0) {
-      const float g = gout[((size_t)b * nchan + lvl * N * N + k) * p.HW + q];
-      const float ax = tt.ax[lane][i], ay = tt.ay[lane][j];
-      const float bx = 1.f - ax, by = 1.f - ay;
-      float *c = w + ry * WS + rx;
-      atomicAdd(c, g * (bx * by));
-      atomicAdd(c + 1, g * (ax * by));
-      atomicAdd(c + WS, g * (bx * ay));
-      atomicAdd(c + WS + 1, g * (ax * ay));
+// add one accumulated window row (staged columns 0..15 of `wrow`, lane-minor) into the query's slice
+template <int PATH>
+__device__ __forceinline__ void flush_row(const float *wrow, float *grow, int ox, int LW, int clo, int chi) {
+  if (PATH == PATH_SECTOR) {
+    const int c0 = ox & ~7, off = ox & 4;   // staged column s sits at loaded column s + off
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      const int x = c0 + 8 * g;
+      if (x < 0 || x >= LW || chi + off < 8 * g || clo + off >= 8 * g + 8) continue;
+      float v[8];
+      ld256(grow + x, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int sidx = 8 * g + k - off;
+        if (sidx >= 0 && sidx < kCols) v[k] += wrow[sidx * 32];
+      }
+      st256(grow + x, v);
+    }
+  } else if (PATH == PATH_VEC4) {
+    const int c0 = ox & ~3;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int x = c0 + 4 * g;
+      if (x < 0 || x >= LW || chi < 4 * g || clo >= 4 * g + 4) continue;
+      float4 v = *reinterpret_cast<float4 *>(grow + x);
+      v.x += wrow[(4 * g) * 32]; v.y += wrow[(4 * g + 1) * 32];
+      v.z += wrow[(4 * g + 2) * 32]; v.w += wrow[(4 * g + 3) * 32];
+      *reinterpret_cast<float4 *>(grow + x) = v;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int x = ox + k;
+      const float a = wrow[k * 32];
+      if (x >= 0 && x < LW && a != 0.f) grow[x] += a;
     }
   }
+}
+
+// Backward of the lookup (what autograd derives for grid_sample): the bilinear weights of every tap,
+// times its output gradient, are added into the query's own slice of the dense gradient pyramid.
+// Same decomposition as the forward kernel: CTA = 4 warps x 32 consecutive queries of one level,
+// lane = query.  Warp w OWNS window rows 3w..3w+2: it gathers every contribution to those rows (in
+// registers when the taps sit on consecutive window positions -- the common case -- else by
+// read-modify-write of its rows of the shared tile), then adds the rows into the slice with
+// sector-sized read-modify-writes.  A slice is touched by exactly one CTA per launch and a row by
+// exactly one warp: no atomics anywhere, deterministic.
+template <int R>
+__global__ void __launch_bounds__(128, 4)
+lookup_bwd_kernel(const LookupParams p, const float *__restrict__ coords,
+                  const float *__restrict__ gout) {
+  constexpr int N = Geo<R>::N, WS = Geo<R>::WS, RPW = (WS + 3) / 4;
+  __shared__ float win[WS * kCols * 32];   // [row][column][lane]
+  __shared__ int tab_r[2 * N][32];
+  __shared__ float tab_a[2 * N][32];
+  const int lvl = blockIdx.x % p.num_levels, q0 = (blockIdx.x / p.num_levels) * QT, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = q0 + lane;
+  const bool q_ok = q < p.HW;
+  const int mode = p.mode, path = p.path[lvl];
+  const int LH = p.LH[lvl], LW = p.LW[lvl];
+  float cx = 0.f, cy = 0.f;
+  if (q_ok) {
+    cx = coords[((size_t)b * 2 + 0) * p.HW + q];
+    cy = coords[((size_t)b * 2 + 1) * p.HW + q];
+  }
+  int xlo, xhi, ylo, yhi;
+  const int ox = window_origin<R>(cx, lvl, xlo, xhi), oy = window_origin<R>(cy, lvl, ylo, yhi);
+  const int shift = path == PATH_SCALAR ? 0 : (ox & 3);
+  const float smx = (float)(LW - 1), smy = (float)(LH - 1);
+  const float ismx = __frcp_rn(smx), ismy = __frcp_rn(smy);
+#pragma unroll 1
+  for (int e = warp; e < 2 * N; e += 4) {
+    const bool isy = e >= N;
+    int rel;
+    float frac;
+    one_tap<R>(isy ? cy : cx, lvl, isy ? e - N : e, isy ? smy : smx, isy ? ismy : ismx, mode, isy ? oy : ox, rel, frac);
+    const int lo = isy ? ylo : xlo, hi = isy ? yhi : xhi;
+    if (rel >= 0 && (rel < lo || rel + 1 > hi)) { rel = -1; frac = 0.f; }   // same rule as the forward
+    tab_r[e][lane] = rel;
+    tab_a[e][lane] = frac;
+  }
   __syncthreads();
-  // add the window into the query's slice (only this CTA touches these slices in this launch)
-  for (int i = threadIdx.x; i < QT * WS; i += blockDim.x) {
-    const int qi = i / WS, r = i - qi * WS;
-    const int qq = q0 + qi;
-    const int y = tt.oy[qi] + r, xo = tt.ox[qi];
-    if (qq < p.HW && y >= 0 && y < LH) {
-      float *dst = gvol + (((size_t)b * p.HW + qq) * LH + y) * LW;
-      const float *src = win + qi * WSTRIDE + r * WS;
+
+  int rxs[N];
+  float axs[N], bxs[N];
+  bool fast = true;   // x and y taps on consecutive window positions
 #pragma unroll
-      for (int c = 0; c < WS; ++c) {
-        const int x = xo + c;
-        if (x >= 0 && x < LW && src[c] != 0.f) dst[x] += src[c];
+  for (int i = 0; i < N; ++i) {
+    rxs[i] = tab_r[i][lane];
+    axs[i] = tab_a[i][lane];
+    bxs[i] = 1.f - axs[i];
+    fast = fast && rxs[i] == rxs[0] + i && rxs[0] >= 0;
+  }
+  const int ry0 = tab_r[N][lane];
+#pragma unroll
+  for (int j = 1; j < N; ++j) fast = fast && tab_r[N + j][lane] == ry0 + j;
+  fast = __all_sync(0xffffffffu, fast && ry0 >= 0);
+  const int nchan = p.num_levels * N * N;
+  const float *gq = gout + ((size_t)b * nchan + (size_t)lvl * N * N) * p.HW + q;
+  float *wl = win + lane;
+
+  if (fast) {
+#pragma unroll 1
+    for (int r = 0; r < RPW; ++r) {
+      const int wr = warp * RPW + r;
+      if (wr >= WS) break;
+      float acc[N + 1];
+#pragma unroll
+      for (int k = 0; k <= N; ++k) acc[k] = 0.f;
+      // row wr collects the upper taps of y offset j = wr - ry0 and the lower taps of j = wr - 1 - ry0
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int j = wr - half - ry0;
+        const bool ok = q_ok && j >= 0 && j < N;
+        const int jj = ok ? j : 0;
+        const float ay = tab_a[N + jj][lane];
+        const float wy = half ? ay : 1.f - ay;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float g = ok ? __ldg(gq + (size_t)(i * N + jj) * p.HW) : 0.f;
+          acc[i] = __fmaf_rn(g, __fmul_rn(bxs[i], wy), acc[i]);
+          acc[i + 1] = __fmaf_rn(g, __fmul_rn(axs[i], wy), acc[i + 1]);
+        }
+      }
+      float *dst = wl + (wr * kCols) * 32;
+#pragma unroll
+      for (int c = 0; c < kCols; ++c) dst[c * 32] = 0.f;
+#pragma unroll
+      for (int k = 0; k <= N; ++k) dst[(shift + rxs[0] + k) * 32] = acc[k];
+    }
+  } else {
+    // general case: this warp's rows are a private accumulator for whatever lands on them
+#pragma unroll 1
+    for (int r = 0; r < RPW; ++r) {
+      const int wr = warp * RPW + r;
+      if (wr >= WS) break;
+#pragma unroll
+      for (int c = 0; c < kCols; ++c) wl[(wr * kCols + c) * 32] = 0.f;
+    }
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+      const int ry = tab_r[N + j][lane];
+      const float ay = tab_a[N + j][lane];
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int row = ry + half;
+        const bool mine = q_ok && ry >= 0 && row >= warp * RPW && row < warp * RPW + RPW && row < WS;
+        const float wy = half ? ay : 1.f - ay;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          if (mine && rxs[i] >= 0) {
+            const float g = __ldg(gq + (size_t)(i * N + j) * p.HW);
+            float *c = wl + (row * kCols + shift + rxs[i]) * 32;
+            c[0] = __fmaf_rn(g, __fmul_rn(bxs[i], wy), c[0]);
+            c[32] = __fmaf_rn(g, __fmul_rn(axs[i], wy), c[32]);
+          }
+        }
       }
     }
+  }
+  __syncwarp();
+  if (!q_ok) return;
+
+  // ---- add this warp's rows into the slice (only rows / sectors the taps can have touched)
+  float *slice = p.glvl[lvl] + ((size_t)b * p.HW + q) * LH * LW;
+  const int clo = shift + xlo, chi = shift + xhi;
+#pragma unroll 1
+  for (int r = 0; r < RPW; ++r) {
+    const int wr = warp * RPW + r, y = oy + wr;
+    if (wr >= WS || wr < ylo || wr > yhi || y < 0 || y >= LH) continue;
+    const float *wrow = wl + (wr * kCols) * 32;
+    float *grow = slice + (size_t)y * LW;
+    if (path == PATH_SECTOR) flush_row<PATH_SECTOR>(wrow, grow, ox, LW, clo, chi);
+    else if (path == PATH_VEC4) flush_row<PATH_VEC4>(wrow, grow, ox, LW, clo, chi);
+    else flush_row<PATH_SCALAR>(wrow, grow, ox, LW, clo, chi);
   }
 }
 
@@ -485,12 +576,16 @@ int b200corr_lookup_backward(float *const *h_grad_levels, int num_levels, const 
   if (int e = fill_params(p, nullptr, h_grad_levels, num_levels, B, H, W, radius, mode, "lookup_backward")) return e;
   if (B == 0) return 0;
   B200_CHECK(coords && grad_out, "lookup_backward: null pointer");
-  dim3 grid((p.HW + QT - 1) / QT, num_levels, B);
+  for (int l = 0; l < num_levels; ++l) {
+    const uintptr_t a = (uintptr_t)p.glvl[l];
+    p.path[l] = (p.LW[l] % 8 == 0 && a % 32 == 0) ? PATH_SECTOR : (p.LW[l] % 4 == 0 && a % 16 == 0) ? PATH_VEC4 : PATH_SCALAR;
+  }
+  dim3 grid(((p.HW + QT - 1) / QT) * num_levels, 1, B);
   switch (radius) {
-    case 1: lookup_bwd_kernel<1><<<grid, 256, 0, stream>>>(p, coords, grad_out); break;
-    case 2: lookup_bwd_kernel<2><<<grid, 256, 0, stream>>>(p, coords, grad_out); break;
-    case 3: lookup_bwd_kernel<3><<<grid, 256, 0, stream>>>(p, coords, grad_out); break;
-    default: lookup_bwd_kernel<4><<<grid, 256, 0, stream>>>(p, coords, grad_out); break;
+    case 1: lookup_bwd_kernel<1><<<grid, 128, 0, stream>>>(p, coords, grad_out); break;
+    case 2: lookup_bwd_kernel<2><<<grid, 128, 0, stream>>>(p, coords, grad_out); break;
+    case 3: lookup_bwd_kernel<3><<<grid, 128, 0, stream>>>(p, coords, grad_out); break;
+    default: lookup_bwd_kernel<4><<<grid, 128, 0, stream>>>(p, coords, grad_out); break;
   }
   B200_LAUNCH_OK("lookup_bwd_kernel");
   return 0;

@@ -224,9 +224,15 @@ class _VolumeFunction(torch.autograd.Function):
         pyramid_backward(gl, B, H, W)
         gvol = gl[0].view(B, H * W, H * W)
         scale = 1.0 / math.sqrt(C)
-        # plain library GEMMs (cuBLAS): dF1 = scale * F2 gvol^T, dF2 = scale * F1 gvol
-        g1 = torch.bmm(fmap2.reshape(B, C, H * W), gvol.transpose(1, 2)).mul_(scale).view_as(fmap1)
-        g2 = torch.bmm(fmap1.reshape(B, C, H * W), gvol).mul_(scale).view_as(fmap2)
+        # plain library GEMMs (cuBLAS): dF1 = scale * F2 gvol^T, dF2 = scale * F1 gvol -- in the precision
+        # the volume itself was built with (TF32 tensor cores for "tf32", exact fp32 for "fp32")
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = block.precision == "tf32"
+        try:
+            g1 = torch.bmm(fmap2.reshape(B, C, H * W), gvol.transpose(1, 2)).mul_(scale).view_as(fmap1)
+            g2 = torch.bmm(fmap1.reshape(B, C, H * W), gvol).mul_(scale).view_as(fmap2)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
         return g1, g2, None
 
 
