@@ -117,6 +117,25 @@ __device__ __forceinline__ void store_row_vec(float *dst, const float (&v)[N], i
   }
 }
 
+// Pooled level whose width is not a multiple of 4 (no 16-byte stores): every lane holds NV consecutive
+// values of ITS query row; scalar stores straight from registers would be 32 scattered 4-byte writes per
+// instruction.  Transpose through the warp's staging tile instead, so that NV consecutive lanes write NV
+// consecutive floats of one row (whole sectors).  `stage` holds 32 x (NV + 1) floats.
+template <int NV>
+__device__ __forceinline__ void store_rows_coalesced(float *stage, const float (&v)[NV], float *level, size_t qbase,
+                                                     int mrow0, int HW, int row_elems, int y, int x, int WL, int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < NV; ++j) stage[lane * (NV + 1) + j] = v[j];
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < NV; ++it) {
+    const int idx = it * 32 + lane, qr = idx / NV, e = idx % NV;
+    if (mrow0 + qr < HW && x + e < WL)
+      level[((qbase + qr) * row_elems) + (size_t)y * WL + x + e] = stage[qr * (NV + 1) + e];
+  }
+}
+
 template <int CTAS>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -326,8 +345,9 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 if (mm < p.HW && y1 < p.LH[0] && xx < p.LW[0])
                   __stcs(reinterpret_cast<float4 *>(p.lvl[0] + (((size_t)bst * p.HW + mm) * p.LH[0] + y1) * p.LW[0] + xx), v);
               }
-            } else if (m_ok && y1 < p.LH[0]) {
-              store_row_vec(p.lvl[0] + (q * p.LH[0] + y1) * p.LW[0] + x1, p1, x1, p.LW[0], false);
+            } else if (y1 < p.LH[0]) {
+              store_rows_coalesced<16>(reinterpret_cast<float *>(ebuf), p1, p.lvl[0], (size_t)bst * p.HW + mrow0, mrow0,
+                                       p.HW, p.LH[0] * p.LW[0], y1, x1, p.LW[0], lane);
             }
           }
           if (r == PH / 2 - 1) {
@@ -336,10 +356,16 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               p2[j] = (((p1prev[2 * j] + p1prev[2 * j + 1]) + p1[2 * j]) + p1[2 * j + 1]) * 0.25f;
-            if (p.lvl[1] && m_ok) {
+            if (p.lvl[1] && m_dbg) {
               const int y2 = y0 / 4 + half, x2 = x0 / 4;
-              if (y2 < p.LH[1])
-                store_row_vec(p.lvl[1] + (q * p.LH[1] + y2) * p.LW[1] + x2, p2, x2, p.LW[1], v2);
+              if (y2 < p.LH[1]) {
+                if (v2) {
+                  if (m_ok) store_row_vec(p.lvl[1] + (q * p.LH[1] + y2) * p.LW[1] + x2, p2, x2, p.LW[1], true);
+                } else {
+                  store_rows_coalesced<8>(reinterpret_cast<float *>(ebuf), p2, p.lvl[1], (size_t)bst * p.HW + mrow0, mrow0,
+                                          p.HW, p.LH[1] * p.LW[1], y2, x2, p.LW[1], lane);
+                }
+              }
             }
             if (p.lvl[2]) {
               // ---- level 3 = mean of the two level-2 rows of this patch: half 0 hands its row over
@@ -362,10 +388,14 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                   p3[j] = (((p2prev[2 * j] + p2prev[2 * j + 1]) + p2[2 * j]) + p2[2 * j + 1]) * 0.25f;
-                if (m_ok) {
-                  const int y3 = y0 / 8, x3 = x0 / 8;
-                  if (y3 < p.LH[2])
-                    store_row_vec(p.lvl[2] + (q * p.LH[2] + y3) * p.LW[2] + x3, p3, x3, p.LW[2], v3);
+                const int y3 = y0 / 8, x3 = x0 / 8;
+                if (y3 < p.LH[2] && m_dbg) {
+                  if (v3) {
+                    if (m_ok) store_row_vec(p.lvl[2] + (q * p.LH[2] + y3) * p.LW[2] + x3, p3, x3, p.LW[2], true);
+                  } else {
+                    store_rows_coalesced<4>(reinterpret_cast<float *>(ebuf), p3, p.lvl[2], (size_t)bst * p.HW + mrow0, mrow0,
+                                            p.HW, p.LH[2] * p.LW[2], y3, x3, p.LW[2], lane);
+                  }
                 }
               }
             }
