@@ -2,6 +2,8 @@
 and the host-only entry points behave (no compute calls here: there is no GPU)."""
 import os
 import re
+import subprocess
+import sys
 
 import pytest
 
@@ -51,3 +53,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference checkout not present")
+def test_reference_model_files_import_this_implementation():
+    """Drop-in without touching the reference: its UNMODIFIED model files resolve the correlation
+    operators to this package once the shims are installed (a subprocess keeps sys.modules clean)."""
+    code = r"""
+import sys, types, warnings
+warnings.filterwarnings("ignore")
+sys.path.insert(0, %r)
+import understanding_flow_robustness_b200 as b200
+b200.install_reference_shims()
+pkg = types.ModuleType("models"); pkg.__path__ = ["/root/reference/models"]; sys.modules["models"] = pkg
+import importlib
+sub = importlib.import_module("models.submodules")           # models/submodules.py:5-16
+assert sub.spatial_correlation_sample is b200.spatial_correlation_sample, "FlowNetC correlate() not redirected"
+raft = importlib.import_module("models.raft.raft")           # models/raft/raft.py:5
+assert raft.CorrBlock is b200.CorrBlock and raft.AlternateCorrBlock is b200.AlternateCorrBlock
+import alt_cuda_corr
+assert alt_cuda_corr.forward is b200.alt_cuda_corr.forward
+print("shims ok")
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "shims ok" in r.stdout, r.stderr[-2000:]
