@@ -54,7 +54,7 @@ extern "C" {
 
 /* precision of the all-pairs contraction */
 #define B200CORR_PREC_TF32 0   /* one tcgen05 kind::tf32 pass, inputs rounded to TF32 (rna)      */
-#define B200CORR_PREC_TF32X3 1 /* reserved: 3-pass split-TF32; not implemented, returns an error */
+#define B200CORR_PREC_TF32X3 1 /* split TF32: lo*hi + hi*lo + hi*hi on the tensor cores, fp32-level accuracy */
 #define B200CORR_PREC_FP32 2   /* exact fp32 FMA accumulation on the CUDA cores (SIMT tile GEMM) */
 
 /* coordinate arithmetic of the lookup */

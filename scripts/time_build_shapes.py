@@ -18,3 +18,16 @@ for (H, W) in ((68, 120), (48, 160), (55, 128), (46, 100)):
         ms = e0.elapsed_time(e1) / 10
         gb = B * (H * W) ** 2 * 4 * (1 + 0.25 + 1 / 16 + 1 / 64) / 1e9
         print(f"{H}x{W} B={B}: build {ms:.4f} ms  {gb / ms * 1e3:.0f} GB/s")
+for prec in ("tf32", "tf32x3", "fp32"):
+    f1 = torch.randn(4, 256, 48, 160, device="cuda"); f2 = torch.randn(4, 256, 48, 160, device="cuda")
+    keep = [None]
+    def build():
+        keep[0] = None
+        keep[0] = raft_corr.allpairs_pyramid(f1, f2, 4, prec)
+    for _ in range(2): build()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): build()
+    e1.record(); torch.cuda.synchronize()
+    print(f"48x160 B=4 precision {prec}: build {e0.elapsed_time(e1) / 5:.4f} ms")

@@ -1,0 +1,72 @@
+"""Edge cases the reference handles implicitly (empty batch, one-pixel maps, a single channel, patches
+larger than the image, ragged sizes) through every entry point; checked against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def test_empty_batch_everywhere():
+    from understanding_flow_robustness_b200 import CorrBlock, AlternateCorrBlock, coords_grid, raft_corr
+    from understanding_flow_robustness_b200 import spatial_correlation_sample
+    a = torch.zeros(0, 8, 6, 8, device="cuda", requires_grad=True)
+    b = torch.zeros(0, 8, 6, 8, device="cuda", requires_grad=True)
+    out = spatial_correlation_sample(a, b, kernel_size=1, patch_size=21, dilation_patch=2)
+    assert tuple(out.shape) == (0, 21, 21, 6, 8)
+    out.sum().backward()
+    assert tuple(a.grad.shape) == (0, 8, 6, 8)
+    f = torch.zeros(0, 8, 8, 8, device="cuda")
+    pyr = raft_corr.allpairs_pyramid(f, f, 3, "tf32")
+    assert [tuple(p.shape) for p in pyr] == [(0, 1, 8, 8), (0, 1, 4, 4), (0, 1, 2, 2)]
+    c = torch.zeros(0, 2, 8, 8, device="cuda")
+    assert tuple(raft_corr.lookup_forward(pyr, c, 2, 8, 8).shape) == (0, 3 * 25, 8, 8)
+    assert tuple(CorrBlock(f, f, 3, 2)(c).shape) == (0, 75, 8, 8)
+    assert tuple(AlternateCorrBlock(f, f, 3, 2)(c).shape) == (0, 75, 8, 8)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 4), (2, 3, 1, 8), (1, 5, 3, 4), (1, 129, 2, 12), (3, 2, 7, 16)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_sampler_tiny_and_oversized_patch(shape):
+    """FlowNetC structure on maps much smaller than the 41-pixel displacement range (most of the
+    21x21 planes are entirely out of bounds), one channel, one row; register-blocked and generic path."""
+    from oracle import sampler_oracle
+    from understanding_flow_robustness_b200 import spatial_correlation_sample
+    rng = np.random.default_rng(sum(shape))
+    in1 = rng.standard_normal(shape).astype(np.float32)
+    in2 = rng.standard_normal(shape).astype(np.float32)
+    a = torch.from_numpy(in1).cuda().requires_grad_()
+    b = torch.from_numpy(in2).cuda().requires_grad_()
+    out = spatial_correlation_sample(a, b, kernel_size=1, patch_size=21, dilation_patch=2)
+    g = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    out.backward(torch.from_numpy(g).cuda())
+    ref = sampler_oracle.forward(in1, in2, 1, 21, 1, 0, 1, 2)
+    r1, r2 = sampler_oracle.backward(in1, in2, g, 1, 21, 1, 0, 1, 2)
+    assert _rel(out.detach().cpu().numpy(), ref) <= 1e-5
+    assert _rel(a.grad.cpu().numpy(), r1) <= 1e-5 and _rel(b.grad.cpu().numpy(), r2) <= 1e-5
+
+
+@pytest.mark.parametrize("hw", [(1, 4), (2, 8), (3, 5), (9, 4)], ids=lambda s: "x".join(map(str, s)))
+def test_raft_tiny_maps(hw):
+    """All-pairs + pyramid + lookup on maps smaller than one tile / one lookup window."""
+    import math
+    from oracle import raft_oracle
+    from understanding_flow_robustness_b200 import coords_grid, raft_corr
+    H, W = hw
+    torch.manual_seed(H * 10 + W)
+    B, C, L, r = 2, 5, 1, 4
+    f1 = torch.randn(B, C, H, W, device="cuda")
+    f2 = torch.randn(B, C, H, W, device="cuda")
+    exact = torch.einsum("bcm,bcn->bmn", f1.double().view(B, C, -1), f2.double().view(B, C, -1)) / math.sqrt(C)
+    for prec, tol in (("fp32", 1e-5), ("tf32", 2e-3)):
+        vol = raft_corr.allpairs_pyramid(f1, f2, L, prec)[0].view(B, H * W, H * W).double()
+        assert float((vol - exact).abs().max()) <= tol * float(exact.abs().max()) + 1e-6
+    pyr = raft_corr.allpairs_pyramid(f1, f2, L, "fp32")
+    coords = coords_grid(B, H, W, "cuda") + 1.5 * torch.randn(B, 2, H, W, device="cuda")
+    out = raft_corr.lookup_forward(pyr, coords, r, H, W, "direct").cpu().numpy()
+    ora = raft_oracle.lookup([p.cpu().numpy() for p in pyr], coords.cpu().numpy(), r, roundtrip=False)
+    assert np.abs(out - ora).max() <= 2e-6 * np.abs(ora).max() + 1e-7

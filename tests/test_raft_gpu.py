@@ -57,7 +57,7 @@ def _torch_corrblock(f1, f2, coords, L, r):
 
 
 @pytest.mark.parametrize("path", RAFT, ids=[os.path.basename(p)[:-4] for p in RAFT])
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x3"])
 def test_pyramid_vs_reference_golden(path, precision):
     from understanding_flow_robustness_b200 import raft_corr
     z = np.load(path)
@@ -72,7 +72,7 @@ def test_pyramid_vs_reference_golden(path, precision):
         ref = z[f"pyr{l}"]
         got = pyr[l].cpu().numpy()
         assert got.shape == ref.shape
-        tol = 1e-5 * _maxabs(z["pyr0"]) if precision == "fp32" else 2.0 ** -10 * absdot + 1e-5 * _maxabs(z["pyr0"])
+        tol = 1e-5 * _maxabs(z["pyr0"]) if precision != "tf32" else 2.0 ** -10 * absdot + 1e-5 * _maxabs(z["pyr0"])
         assert _maxabs(got - ref) <= tol, (l, _maxabs(got - ref), tol)
 
 
@@ -216,9 +216,15 @@ def test_tcgen05_volume_ragged_shapes(shape):
         ref = F.avg_pool2d(ref, 2, stride=2)
         assert pyr[l].shape == ref.shape
         assert float((pyr[l] - ref).abs().max()) <= 2e-6 * float(v0.abs().max()) + 1e-7, l
-    # exact kernel agrees with the fp64 contraction to fp32 accuracy
+    # exact kernel agrees with the fp64 contraction to fp32 accuracy, and so does split TF32 (lo*hi + hi*lo +
+    # hi*hi on the tensor cores: the dropped lo*lo term is 2^-22 relative per product)
     e32 = raft_corr.allpairs_pyramid(f1, f2, 1, "fp32")[0].view(B, H * W, H * W).double()
     assert float((e32 - exact).abs().max()) <= 1e-5 * float(exact.abs().max())
+    x3 = raft_corr.allpairs_pyramid(f1, f2, L, "tf32x3")
+    v3 = x3[0].view(B, H * W, H * W).double()
+    bound3 = 2.0 ** -20 * torch.einsum("bcm,bcn->bmn", a.abs(), b.abs()) / math.sqrt(C) + 2e-6 * float(exact.abs().max())
+    assert bool(((v3 - exact).abs() <= bound3).all()), float(((v3 - exact).abs() - bound3).max())
+    assert [tuple(t.shape) for t in x3] == [tuple(t.shape) for t in pyr]
 
 
 def test_corrblock_end_to_end_and_autograd():

@@ -34,6 +34,9 @@
 //      box: slower), 256-bit stores straight from registers (32 sectors per instruction: 1.8 TB/s),
 //      a cluster-scope release on the TMEM hand-over (puts a MEMBAR.GPU in front of every arrival).
 //      B200CORR_ALLPAIRS_CTAS=1 selects the single-CTA variant of the same kernel.
+//   Precision TF32X3: the same kernel run as a K-extended GEMM over the split operands x = hi + lo
+//      (both TF32): passes lo(f1)*hi(f2), hi*lo, hi*hi accumulate into the same TMEM tile -- three times
+//      the MMAs, fp32-level accuracy (the dropped lo*lo term is 2^-22 relative per product).
 //   Precision FP32 (exact, also the path for W % 4 != 0): a plain SIMT tile GEMM + pooling kernels.
 //
 // Error bound of the TF32 path (documented in DESIGN.md, asserted in tests): inputs are rounded to
@@ -47,9 +50,11 @@ namespace {
 using namespace b200dev;
 
 // ------------------------------------------------------------------------------ prep (transpose)
-// in [B][C][HW] -> out [B][HW][Cp], tf32-rounded, channels >= C zero
+// in [B][C][HW] -> out [B][HW][Cp], tf32-rounded, channels >= C zero.  With out_lo (TF32x3): the
+// residual x - tf32(x), itself rounded to TF32, so that x = hi + lo to ~2^-22 relative.
 __global__ void __launch_bounds__(256)
-prep_kmajor_tf32_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int Cp, int HW) {
+prep_kmajor_tf32_kernel(const float *__restrict__ in, float *__restrict__ out, float *__restrict__ out_lo, int C,
+                        int Cp, int HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -59,13 +64,17 @@ prep_kmajor_tf32_kernel(const float *__restrict__ in, float *__restrict__ out, i
     const int c = c0 + ty + 8 * i, p = p0 + tx;
     float v = 0.f;
     if (c < C && p < HW) v = in[((size_t)b * C + c) * HW + p];
-    tile[ty + 8 * i][tx] = to_tf32_rna(v);
+    tile[ty + 8 * i][tx] = v;
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int p = p0 + ty + 8 * i, c = c0 + tx;
-    if (p < HW && c < Cp) out[((size_t)b * HW + p) * Cp + c] = tile[tx][ty + 8 * i];
+    if (p < HW && c < Cp) {
+      const float v = tile[tx][ty + 8 * i], hi = to_tf32_rna(v);
+      out[((size_t)b * HW + p) * Cp + c] = hi;
+      if (out_lo) out_lo[((size_t)b * HW + p) * Cp + c] = to_tf32_rna(v - hi);
+    }
   }
 }
 
@@ -93,6 +102,7 @@ struct Cfg {
 
 struct Params {
   int B, HW, H, W, KB;       // KB = Cp / 32
+  int passes;                // 1: TF32.  3: TF32x3 -- the k loop runs over lo*hi, hi*lo, hi*hi (K-extended GEMM)
   int MT, NTY, NTX;          // tile counts (MT counts 128*CTAS-row blocks)
   float scale;
   int debug;                 // B200CORR_DEBUG bits (diagnostics): 1 skip level-0 stores, 2 skip pooled stores
@@ -139,6 +149,7 @@ __device__ __forceinline__ void store_rows_coalesced(float *stage, const float (
 template <int CTAS>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapBlo,
                    const tc::Params p) {
   using namespace tc;
   using C = Cfg<CTAS>;
@@ -164,6 +175,10 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
+    if (p.passes == 3) {
+      tma_prefetch_desc(&mapAlo);
+      tma_prefetch_desc(&mapBlo);
+    }
     for (int s = 0; s < NST; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -201,19 +216,22 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       for (int t = unit; t < total; t += nunits) {
         const int nt = t % NT, mt = (t / NT) % p.MT, b = t / (NT * p.MT);
         const int y0 = (nt / p.NTX) * PH, x0 = (nt % p.NTX) * PW, m0 = (mt * CTAS + (int)rank) * BM;
-        for (int kb = 0; kb < p.KB; ++kb, ++it) {
+        for (int kk = 0; kk < p.KB * p.passes; ++kk, ++it) {
+          // TF32x3: pass 0 = lo(f1) * hi(f2), pass 1 = hi * lo, pass 2 = hi * hi (small terms first)
+          const int pass = p.passes == 1 ? 2 : kk / p.KB, kb = kk - (p.passes == 1 ? 0 : pass * p.KB);
+          const CUtensorMap *ma = pass == 0 ? &mapAlo : &mapA, *mb = pass == 1 ? &mapBlo : &mapB;
           const int st = it % NST;
           mbar_wait(&empty_bar[st], ((it / NST) & 1) ^ 1);
           uint8_t *a = sm + st * STAGE_BYTES;
           if (CTAS == 2) {
             // one arrival (the leader's) expects the bytes of both CTAs
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[st], 2 * STAGE_BYTES);
-            tma_load_3d_2cta(a, &mapA, full_cluster[st], kb * BK, m0, b);
-            tma_load_4d_2cta(a + A_BYTES, &mapB, full_cluster[st], kb * BK, x0, y0 + (int)rank * (PH / 2), b);
+            tma_load_3d_2cta(a, ma, full_cluster[st], kb * BK, m0, b);
+            tma_load_4d_2cta(a + A_BYTES, mb, full_cluster[st], kb * BK, x0, y0 + (int)rank * (PH / 2), b);
           } else {
             mbar_arrive_expect_tx(&full_bar[st], STAGE_BYTES);
-            tma_load_3d(a, &mapA, &full_bar[st], kb * BK, m0, b);
-            tma_load_4d(a + A_BYTES, &mapB, &full_bar[st], kb * BK, x0, y0, b);
+            tma_load_3d(a, ma, &full_bar[st], kb * BK, m0, b);
+            tma_load_4d(a + A_BYTES, mb, &full_bar[st], kb * BK, x0, y0, b);
           }
         }
       }
@@ -228,7 +246,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         mbar_wait(&tempty_bar[buf], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < p.KB; ++kb, ++it) {
+        for (int kb = 0; kb < p.KB * p.passes; ++kb, ++it) {
           const int st = it % NST;
           mbar_wait(&full_bar[st], (it / NST) & 1);
           tc_fence_after();
@@ -494,7 +512,7 @@ extern "C" {
 size_t b200corr_allpairs_workspace_bytes(int B, int C, int H, int W, int precision) {
   if (precision == B200CORR_PREC_FP32) return 0;
   const size_t Cp = (size_t)(C + 31) / 32 * 32;
-  return 2 * (size_t)B * H * W * Cp * sizeof(float);
+  return (precision == B200CORR_PREC_TF32X3 ? 4 : 2) * (size_t)B * H * W * Cp * sizeof(float);
 }
 
 int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_levels,
@@ -503,8 +521,8 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK(num_levels >= 1 && num_levels <= 8, "allpairs_pyramid: num_levels must be in [1, 8]");
   B200_CHECK(B >= 0 && C >= 1 && H >= 1 && W >= 1, "allpairs_pyramid: bad sizes");
-  B200_CHECK(precision == B200CORR_PREC_TF32 || precision == B200CORR_PREC_FP32,
-             "allpairs_pyramid: precision %d not available (TF32 = 0, FP32 = 2)", precision);
+  B200_CHECK(precision == B200CORR_PREC_TF32 || precision == B200CORR_PREC_TF32X3 || precision == B200CORR_PREC_FP32,
+             "allpairs_pyramid: precision %d not available (TF32 = 0, TF32X3 = 1, FP32 = 2)", precision);
   if (B == 0) return 0;
   B200_CHECK(f1 && f2 && h_levels && h_levels[0], "allpairs_pyramid: null pointer");
   const int HW = H * W;
@@ -531,24 +549,30 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
       if (e && atoi(e) == 1) ctas = 1;
       if (b200::num_sms() % 2) ctas = 1;
     }
-    const size_t need = 2 * (size_t)B * HW * Cp * sizeof(float);
+    const bool x3 = precision == B200CORR_PREC_TF32X3;
+    const size_t need = (x3 ? 4 : 2) * (size_t)B * HW * Cp * sizeof(float);
     B200_CHECK(workspace && workspace_bytes >= need,
                "allpairs_pyramid: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     B200_CHECK(((uintptr_t)workspace & 127) == 0 && ((uintptr_t)h_levels[0] & 15) == 0,
                "allpairs_pyramid: workspace must be 128-byte and level 0 16-byte aligned");
-    float *f1t = (float *)workspace, *f2t = f1t + (size_t)B * HW * Cp;
+    const size_t nfeat = (size_t)B * HW * Cp;
+    float *f1t = (float *)workspace, *f2t = f1t + nfeat;
+    float *f1lo = x3 ? f2t + nfeat : nullptr, *f2lo = x3 ? f1lo + nfeat : nullptr;
     dim3 pgrid((HW + 31) / 32, Cp / 32, B);
-    prep_kmajor_tf32_kernel<<<pgrid, 256, 0, stream>>>(f1, f1t, C, Cp, HW);
+    prep_kmajor_tf32_kernel<<<pgrid, 256, 0, stream>>>(f1, f1t, f1lo, C, Cp, HW);
     B200_LAUNCH_OK("prep_kmajor_tf32_kernel");
-    prep_kmajor_tf32_kernel<<<pgrid, 256, 0, stream>>>(f2, f2t, C, Cp, HW);
+    prep_kmajor_tf32_kernel<<<pgrid, 256, 0, stream>>>(f2, f2t, f2lo, C, Cp, HW);
     B200_LAUNCH_OK("prep_kmajor_tf32_kernel");
 
-    CUtensorMap mapA, mapB;
+    CUtensorMap mapA, mapB, mapAlo, mapBlo;
+    for (int which = 0; which < (x3 ? 2 : 1); ++which) {
+      CUtensorMap &mapA_ = which ? mapAlo : mapA, &mapB_ = which ? mapBlo : mapB;
+      const float *f1t_ = which ? f1lo : f1t, *f2t_ = which ? f2lo : f2t;
     {
       const uint64_t dims[3] = {(uint64_t)Cp, (uint64_t)HW, (uint64_t)B};
       const uint64_t str[3] = {4, (uint64_t)Cp * 4, (uint64_t)HW * Cp * 4};
       const uint32_t box[3] = {tc::BK, tc::BM, 1};
-      if (int e = b200::make_tensor_map(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, f1t, dims, str, box,
+      if (int e = b200::make_tensor_map(&mapA_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, f1t_, dims, str, box,
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
         return e;
     }
@@ -556,12 +580,15 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
       const uint64_t dims[4] = {(uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)B};
       const uint64_t str[4] = {4, (uint64_t)Cp * 4, (uint64_t)W * Cp * 4, (uint64_t)HW * Cp * 4};
       const uint32_t box[4] = {tc::BK, tc::PW, (uint32_t)(tc::PH / ctas), 1};
-      if (int e = b200::make_tensor_map(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, f2t, dims, str, box,
+      if (int e = b200::make_tensor_map(&mapB_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, f2t_, dims, str, box,
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
         return e;
     }
+    }
+    if (!x3) { mapAlo = mapA; mapBlo = mapB; }
     tc::Params p;
     p.B = B; p.HW = HW; p.H = H; p.W = W; p.KB = Cp / 32;
+    p.passes = x3 ? 3 : 1;
     p.MT = (HW + tc::BM * ctas - 1) / (tc::BM * ctas);
     p.NTY = (H + tc::PH - 1) / tc::PH;
     p.NTX = (W + tc::PW - 1) / tc::PW;
@@ -594,12 +621,12 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      B200_CUDA(cudaLaunchKernelEx(&cfg, allpairs_tc_kernel<2>, mapA, mapB, p));
+      B200_CUDA(cudaLaunchKernelEx(&cfg, allpairs_tc_kernel<2>, mapA, mapB, mapAlo, mapBlo, p));
     } else {
       static bool attr_done[64] = {};  // per device
       if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel<1>, tc::Cfg<1>::SMEM_BYTES, attr_done)) return e;
       const int grid = total < b200::num_sms() ? total : b200::num_sms();
-      allpairs_tc_kernel<1><<<grid, tc::THREADS, tc::Cfg<1>::SMEM_BYTES, stream>>>(mapA, mapB, p);
+      allpairs_tc_kernel<1><<<grid, tc::THREADS, tc::Cfg<1>::SMEM_BYTES, stream>>>(mapA, mapB, mapAlo, mapBlo, p);
     }
     B200_LAUNCH_OK("allpairs_tc_kernel");
   }

@@ -550,8 +550,8 @@ int b200corr_lookup_forward(const float *const *h_levels, int num_levels, const 
                             float *out, int B, int H, int W, int radius, int mode, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LookupParams p;
+  if (B == 0) return 0;   // empty tensors have no storage: nothing to validate, nothing to do
   if (int e = fill_params(p, h_levels, nullptr, num_levels, B, H, W, radius, mode, "lookup_forward")) return e;
-  if (B == 0) return 0;
   B200_CHECK(coords && out, "lookup_forward: null pointer");
   for (int l = 0; l < num_levels; ++l) {
     const uintptr_t a = (uintptr_t)p.lvl[l];
@@ -573,8 +573,8 @@ int b200corr_lookup_backward(float *const *h_grad_levels, int num_levels, const 
                              void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LookupParams p;
-  if (int e = fill_params(p, nullptr, h_grad_levels, num_levels, B, H, W, radius, mode, "lookup_backward")) return e;
   if (B == 0) return 0;
+  if (int e = fill_params(p, nullptr, h_grad_levels, num_levels, B, H, W, radius, mode, "lookup_backward")) return e;
   B200_CHECK(coords && grad_out, "lookup_backward: null pointer");
   for (int l = 0; l < num_levels; ++l) {
     const uintptr_t a = (uintptr_t)p.glvl[l];
@@ -595,8 +595,8 @@ int b200corr_pyramid_backward(float *const *h_grad_levels, int num_levels, int B
                               void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LookupParams p;
-  if (int e = fill_params(p, nullptr, h_grad_levels, num_levels, B, H, W, 1, 0, "pyramid_backward")) return e;
   if (B == 0) return 0;
+  if (int e = fill_params(p, nullptr, h_grad_levels, num_levels, B, H, W, 1, 0, "pyramid_backward")) return e;
   const long long Q = (long long)B * H * W;
   for (int l = num_levels - 1; l >= 1; --l) {
     const long long total = Q * p.LH[l - 1] * p.LW[l - 1];

@@ -13,7 +13,8 @@ layout and channel order) and the pybind surface of models/alt_cuda_corr/correla
 
 Differences from the reference, all deliberate:
   * the volume is computed from TF32-rounded features by default (`precision="tf32"`; bound in
-    DESIGN.md); `precision="fp32"` selects the exact CUDA-core kernel;
+    DESIGN.md); `precision="tf32x3"` runs the split-TF32 contraction (fp32-level accuracy, still on the
+    tensor cores), `precision="fp32"` the exact CUDA-core kernel;
   * both blocks are differentiable w.r.t. the feature maps (the reference's AlternateCorrBlock is
     forward-only because nothing wraps alt_cuda_corr.backward); coordinates get no gradient, as in
     the reference (raft.py:188 detaches them, correlation_kernel.cu:307 returns zeros);
@@ -29,7 +30,7 @@ import torch.nn.functional as F
 from . import _lib
 from .spatial_correlation_sampler import spatial_correlation_sample
 
-PRECISIONS = {"tf32": 0, "fp32": 2}
+PRECISIONS = {"tf32": 0, "tf32x3": 1, "fp32": 2}
 LOOKUP_MODES = {"grid_sample": 0, "direct": 1}
 
 
@@ -340,5 +341,5 @@ class AlternateCorrBlock:
             corr = _AltCorrFunction.apply(self._f1, self._f2[i], coords_i, self.radius)
             corr_list.append(corr.squeeze(1))
         corr = torch.stack(corr_list, dim=1)
-        corr = corr.reshape(B, -1, H, W)
+        corr = corr.reshape(B, self.num_levels * (2 * self.radius + 1) ** 2, H, W)   # (-1 is ambiguous for B = 0)
         return corr / math.sqrt(dim)
