@@ -70,3 +70,37 @@ def test_raft_tiny_maps(hw):
     out = raft_corr.lookup_forward(pyr, coords, r, H, W, "direct").cpu().numpy()
     ora = raft_oracle.lookup([p.cpu().numpy() for p in pyr], coords.cpu().numpy(), r, roundtrip=False)
     assert np.abs(out - ora).max() <= 2e-6 * np.abs(ora).max() + 1e-7
+
+
+def test_cuda_graph_capture_of_the_operators():
+    """Every operator launches on the current stream with caller-owned memory only, so a step can be
+    captured into a CUDA graph and replayed on new data (what bench.py times)."""
+    from understanding_flow_robustness_b200 import backend, coords_grid, raft_corr
+    torch.manual_seed(0)
+    q = (1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1)
+    a = torch.randn(2, 128, 12, 32, device="cuda")
+    b = torch.randn(2, 128, 12, 32, device="cuda")
+    g = torch.randn(2, 21, 21, 12, 32, device="cuda")
+    f1 = torch.randn(1, 64, 16, 32, device="cuda")
+    f2 = torch.randn(1, 64, 16, 32, device="cuda")
+    c = coords_grid(1, 16, 32, "cuda") + 2.0 * torch.randn(1, 2, 16, 32, device="cuda")
+    with torch.no_grad():
+        backend.forward(a, b, *q); backend.backward(a, b, g, *q)          # warm-up: attributes, plan cache
+        raft_corr.lookup_forward(raft_corr.allpairs_pyramid(f1, f2, 3, "tf32"), c, 3, 16, 32)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = backend.forward(a, b, *q)
+            g1, g2 = backend.backward(a, b, g, *q)
+            pyr = raft_corr.allpairs_pyramid(f1, f2, 3, "tf32")
+            look = raft_corr.lookup_forward(pyr, c, 3, 16, 32)
+        for t in (a, b, g, f1, f2):
+            t.normal_()                                                   # new data in the captured buffers
+        graph.replay()
+        torch.cuda.synchronize()
+        got = [t.clone() for t in (out, g1, g2, look)]
+        ref_out = backend.forward(a, b, *q)
+        r1, r2 = backend.backward(a, b, g, *q)
+        ref_look = raft_corr.lookup_forward(raft_corr.allpairs_pyramid(f1, f2, 3, "tf32"), c, 3, 16, 32)
+    for x, y in zip(got, (ref_out, r1, r2, ref_look)):
+        assert torch.equal(x, y)
