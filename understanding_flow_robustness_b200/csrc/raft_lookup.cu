@@ -27,10 +27,10 @@
 // back as e.g. 79.99999 exactly as in the reference.  Mode B200CORR_LOOKUP_DIRECT samples at the
 // pixel coordinate itself (what alt_cuda_corr does).
 //
-// Backward (what autograd derives for the reference): the bilinear weights
-// are scattered into the query's own slice of a dense per-level gradient volume.  Each slice is
-// touched by exactly one CTA per launch, so the scatter is first reduced in shared memory and then
-// added with plain coalesced read-modify-writes -- no global atomics.  Coordinates get no gradient
+// Backward (what autograd derives for the reference): the bilinear weights,
+// times the output gradient, are added into the query's own slice of a dense per-level gradient
+// volume -- same CTA / lane mapping as the forward, each warp owning three window rows, so neither
+// shared nor global atomics are needed (see lookup_bwd_kernel).  Coordinates get no gradient
 // (raft.py:188 detaches them).
 #include "common.cuh"
 
@@ -43,33 +43,14 @@ struct LookupParams {
   const float *lvl[kMaxLevels];
   float *glvl[kMaxLevels];
   int LH[kMaxLevels], LW[kMaxLevels];
-  int path[kMaxLevels];  // forward staging flavour per level
+  int path[kMaxLevels];  // access flavour per level (sector / 16-byte / scalar), from width and alignment
   int num_levels, B, HW, radius, mode;
 };
-
-// pixel coordinate the reference ends up sampling at, along one axis of size `size`
-__device__ __forceinline__ float sample_coord(float c, int lvl, int off, int size, int mode) {
-  // corr.py:84-86: centroid / 2**i  + delta   (division by a power of two is exact)
-  const float x = __fadd_rn(__fmul_rn(c, 1.0f / (float)(1 << lvl)), (float)off);
-  if (mode == B200CORR_LOOKUP_DIRECT) return x;
-  const float sm1 = (float)(size - 1);
-  // utils.py:66: 2 * x / (W - 1) - 1
-  const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, x), sm1), 1.0f);
-  // grid_sampler_unnormalize, align_corners=True
-  return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), sm1);
-}
 
 template <int R>
 struct Geo {
   static constexpr int N = 2 * R + 1;      // taps per axis
-  static constexpr int WS = 2 * R + 4;     // staged window per axis
-  static constexpr int WSTRIDE = WS * WS + 1;
-  // vector path (level width % 4 == 0): a window row is fetched as NV4 aligned float4 covering
-  // [ox & ~3, ...) and stored shifted by (ox & 3); odd row / query pitches keep both the staging
-  // stores (lane = window row) and the sampling loads (lane = query) bank-conflict free
-  static constexpr int NV4 = (WS + 3 + 3) / 4;
-  static constexpr int VROW = WS | 1;
-  static constexpr int VSTRIDE = (WS * VROW) | 1;
+  static constexpr int WS = 2 * R + 4;     // window per axis: the taps + one guard row/column on either side
 };
 
 // 256-bit / 128-bit read-only loads that do not pollute L1 (every sector is used exactly once)
@@ -104,7 +85,12 @@ __device__ __forceinline__ float div_by(float a, float b, float y) {
   return __fmaf_rn(r, y, q);
 }
 
-// sample_coord() with the reciprocal of (size - 1) hoisted: same value, a third of the instructions
+// Pixel coordinate the reference ends up sampling at, along one axis of size sm1 + 1:
+//   corr.py:84-86       centroid / 2**i + delta          (division by a power of two is exact)
+//   utils.py:66         g = 2 * x / (W - 1) - 1
+//   grid_sampler_unnormalize, align_corners=True:  ((g + 1) / 2) * (W - 1)
+// every operation rounded separately in fp32 (no FMA contraction); the one real division uses the
+// hoisted reciprocal of (size - 1): same value, a third of the instructions.
 __device__ __forceinline__ float sample_coord_fast(float c, int lvl, int off, float sm1, float inv_sm1, int mode) {
   const float x = __fadd_rn(__fmul_rn(c, 1.0f / (float)(1 << lvl)), (float)off);
   if (mode == B200CORR_LOOKUP_DIRECT) return x;
