@@ -9,18 +9,23 @@ from collections import Counter
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+    which = int(sys.argv[3]) if len(sys.argv) > 3 else -1   # kernel index inside the report
     txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr = None
-    data = []
+    tables = []
     for r in rows:
+        if r and r[0] == 'Kernel Name':
+            print('kernel:', r[1][:90])
         if r and r[0] == 'Address':
             hdr = r
-            data = []
+            tables.append([])
             continue
         if hdr and len(r) == len(hdr):
-            data.append(r)
+            tables[-1].append(r)
+    data = tables[which]
+    print(f'-- table {which} of {len(tables)}')
     ia, isrc, isamp, iex = hdr.index('Address'), hdr.index('Source'), hdr.index('# Samples'), hdr.index('Instructions Executed')
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
     tot_s = sum(int(r[isamp]) for r in data)
