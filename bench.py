@@ -549,6 +549,17 @@ def raft_bench(dev):
         gather_grows = float(gr.value)
         alt = AlternateCorrBlock(f1, f2, c["levels"], c["radius"])
         alt_ms = timed(lambda: alt(coords[0]), 3)
+        # extra rows of the same path (not part of ms/iter): lookup backward into a resident gradient pyramid,
+        # and the volume in split-TF32 (fp32-level accuracy on the tensor cores)
+        from understanding_flow_robustness_b200 import raft_corr
+        glv = [torch.zeros_like(v) for v in blk[0].corr_pyramid]
+        gout = torch.randn(B, c["levels"] * (2 * c["radius"] + 1) ** 2, H, W, device=dev)
+        lbwd_fn, _ = graphed(lambda: raft_corr.lookup_backward(glv, coords[0], gout, c["radius"], H, W))
+        lookup_bwd_ms = timed(lbwd_fn, 10)
+        del glv, gout
+        blk[0] = None
+        x3_fn, _ = graphed(lambda: raft_corr.allpairs_pyramid(f1, f2, c["levels"], "tf32x3"))
+        build_x3_ms = timed(x3_fn, 3)
     HW = H * W
     vol_bytes = B * (4 * HW * HW * (1 + 0.25 + 1 / 16 + 1 / 64) + 2 * C * HW * 4)
     look_bytes = B * (324 * HW * 4 + 4 * HW * 100 * 4)
@@ -561,6 +572,7 @@ def raft_bench(dev):
     src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     return {"metric": "RAFT corr+lookup ms/iter", "ms_per_iter": (build_ms + c["iters"] * look_ms) / c["iters"],
             "build_ms": build_ms, "lookup_ms": look_ms, "alt_corr_ms_per_iter": alt_ms,
+            "lookup_backward_ms": lookup_bwd_ms, "build_tf32x3_ms": build_x3_ms,
             "config": f"B={B}, {C}x{H}x{W}, {c['levels']} levels, radius {c['radius']}, {c['iters']} lookups, TF32 volume",
             "timed_loop": {"build": how_build, "lookups": how_look},
             "roofline_build": {"bound": "hbm", "achieved": vol_bytes / (build_ms * 1e-3) / 1e9, "peak": hbm,
