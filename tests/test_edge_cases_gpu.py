@@ -104,3 +104,37 @@ def test_cuda_graph_capture_of_the_operators():
         ref_look = raft_corr.lookup_forward(raft_corr.allpairs_pyramid(f1, f2, 3, "tf32"), c, 3, 16, 32)
     for x, y in zip(got, (ref_out, r1, r2, ref_look)):
         assert torch.equal(x, y)
+
+
+def test_caller_owned_output_buffers_and_host_pipeline():
+    """backend.forward/backward(out=...) write into caller-owned tensors (what the C ABI does anyway);
+    the host-buffer pipeline built on it reproduces the plain operator."""
+    from understanding_flow_robustness_b200 import backend
+    from understanding_flow_robustness_b200.host_pipeline import SamplerHostPipeline
+    torch.manual_seed(1)
+    q = (1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1)
+    shape = (2, 32, 8, 16)
+    a, b = torch.randn(*shape, device="cuda"), torch.randn(*shape, device="cuda")
+    g = torch.randn(2, 21, 21, 8, 16, device="cuda")
+    ref_out = backend.forward(a, b, *q)
+    r1, r2 = backend.backward(a, b, g, *q)
+    out, g1, g2 = torch.empty_like(ref_out), torch.empty_like(a), torch.empty_like(b)
+    assert backend.forward(a, b, *q, out=out) is out
+    backend.backward(a, b, g, *q, out=(g1, g2))
+    assert torch.equal(out, ref_out) and torch.equal(g1, r1) and torch.equal(g2, r2)
+    with pytest.raises(RuntimeError):
+        backend.forward(a, b, *q, out=torch.empty(2, 21, 21, 8, 8, device="cuda"))
+    with pytest.raises(RuntimeError):
+        backend.backward(a, b, g, *q, out=(g1, torch.empty(1, device="cuda")))
+    pipe = SamplerHostPipeline(shape, q, torch.device("cuda"))
+    hosts = []
+    for i in range(5):   # more batches than slots
+        h = [torch.randn(*shape).pin_memory(), torch.randn(*shape).pin_memory(), torch.randn(2, 21, 21, 8, 16).pin_memory(),
+             torch.empty(2, 21, 21, 8, 16).pin_memory(), torch.empty(*shape).pin_memory(), torch.empty(*shape).pin_memory()]
+        pipe.submit(*h)
+        hosts.append(h)
+    pipe.synchronize()
+    for h in hosts:
+        o = backend.forward(h[0].cuda(), h[1].cuda(), *q)
+        x1, x2 = backend.backward(h[0].cuda(), h[1].cuda(), h[2].cuda(), *q)
+        assert torch.equal(h[3].cuda(), o) and torch.equal(h[4].cuda(), x1) and torch.equal(h[5].cuda(), x2)

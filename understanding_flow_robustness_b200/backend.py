@@ -39,7 +39,7 @@ def output_size(size, pad, kernel, dilation, stride):
 
 
 def forward(input1, input2, kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
-            dilation_patchH, dilation_patchW, dH, dW):
+            dilation_patchH, dilation_patchW, dH, dW, out=None):
     dt = _check_inputs("correlation forward", input1, input2)
     if input1.dim() != 4 or input1.shape != input2.shape:
         raise RuntimeError("correlation forward: input1 and input2 must both be (B, C, H, W) of the same shape")
@@ -48,7 +48,11 @@ def forward(input1, input2, kH, kW, patchH, patchW, padH, padW, dilationH, dilat
     oW = output_size(W, padW, kW, dilationW, dW)
     if oH < 0 or oW < 0:
         raise RuntimeError("correlation forward: kernel does not fit the padded input")
-    out = torch.empty((B, patchH, patchW, oH, oW), dtype=input1.dtype, device=input1.device)
+    if out is None:
+        out = torch.empty((B, patchH, patchW, oH, oW), dtype=input1.dtype, device=input1.device)
+    elif (tuple(out.shape) != (B, patchH, patchW, oH, oW) or out.dtype != input1.dtype or out.device != input1.device
+          or not out.is_contiguous()):
+        raise RuntimeError("correlation forward: `out` must be a contiguous (B, patchH, patchW, oH, oW) tensor like the inputs")
     with torch.cuda.device(input1.device):
         code = _lib.lib().b200corr_sampler_forward(
             _lib.ptr(input1), _lib.ptr(input2), _lib.ptr(out), None, 0, B, C, H, W, kH, kW, patchH,
@@ -82,7 +86,7 @@ def _backward_plan(device, B, C, H, W, hyper, dt):
 
 
 def backward(input1, input2, grad_output, kH, kW, patchH, patchW, padH, padW, dilationH, dilationW,
-             dilation_patchH, dilation_patchW, dH, dW):
+             dilation_patchH, dilation_patchW, dH, dW, out=None):
     grad_output = grad_output.contiguous()
     dt = _check_inputs("correlation backward", input1, input2, grad_output)
     B, C, H, W = input1.shape
@@ -91,8 +95,14 @@ def backward(input1, input2, grad_output, kH, kW, patchH, patchW, padH, padW, di
     if tuple(grad_output.shape) != (B, patchH, patchW, oH, oW):
         raise RuntimeError(f"correlation backward: grad_output shape {tuple(grad_output.shape)} != "
                            f"{(B, patchH, patchW, oH, oW)}")
-    g1 = torch.empty_like(input1)
-    g2 = torch.empty_like(input2)
+    if out is None:
+        g1 = torch.empty_like(input1)
+        g2 = torch.empty_like(input2)
+    else:
+        g1, g2 = out
+        for g in (g1, g2):
+            if g.shape != input1.shape or g.dtype != input1.dtype or g.device != input1.device or not g.is_contiguous():
+                raise RuntimeError("correlation backward: `out` must be two contiguous tensors like input1")
     hyper = (kH, kW, patchH, patchW, padH, padW, dilationH, dilationW, dilation_patchH, dilation_patchW, dH, dW)
     with torch.cuda.device(input1.device):
         plan = _backward_plan(input1.device, B, C, H, W, hyper, dt)

@@ -22,11 +22,12 @@ class SamplerHostPipeline:
         self.depth = depth
         mk = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
         self.dev_in = [(mk(B, C, H, W), mk(B, C, H, W), mk(B, P1, P2, oH, oW)) for _ in range(depth)]
+        # outputs live in the slot too: no allocator traffic (and no cudaMalloc) in steady state
+        self.dev_out = [(mk(B, P1, P2, oH, oW), mk(B, C, H, W), mk(B, C, H, W)) for _ in range(depth)]
         self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(device) for _ in range(3))
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]       # inputs of slot landed
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]     # kernels of slot finished
         self.ev_free = [torch.cuda.Event() for _ in range(depth)]     # outputs of slot copied out
-        self.pending = [None] * depth
         self.n = 0
 
     def submit(self, h_in1, h_in2, h_gout, h_out, h_g1, h_g2):
@@ -44,8 +45,9 @@ class SamplerHostPipeline:
             self.s_compute.wait_event(self.ev_in[k])
             if self.n >= self.depth:
                 self.s_compute.wait_event(self.ev_free[k])  # previous outputs of this slot were copied out
-            out = backend.forward(d1, d2, *self.hyper)
-            g1, g2 = backend.backward(d1, d2, dg, *self.hyper)
+            out, g1, g2 = self.dev_out[k]
+            backend.forward(d1, d2, *self.hyper, out=out)
+            backend.backward(d1, d2, dg, *self.hyper, out=(g1, g2))
             self.ev_done[k].record(self.s_compute)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_done[k])
@@ -53,9 +55,6 @@ class SamplerHostPipeline:
             h_g1.copy_(g1, non_blocking=True)
             h_g2.copy_(g2, non_blocking=True)
             self.ev_free[k].record(self.s_out)
-        for t in (out, g1, g2):
-            t.record_stream(self.s_out)
-        self.pending[k] = (out, g1, g2)
         self.n += 1
 
     def synchronize(self):
