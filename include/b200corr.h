@@ -126,10 +126,25 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
                               int num_levels, int B, int C, int H, int W, float scale,
                               int precision, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Same with maps of different sizes: f1 [B,C,H1,W1] (queries), f2 [B,C,H2,W2] (keys); level l has shape
+ * (B*H1*W1, 1, H2_l, W2_l).  What AlternateCorrBlock needs for its pooled key maps (corr.py:114-118).
+ * Tensor-core precisions only (TF32, TF32X3), W2 % 4 == 0. */
+size_t b200corr_allpairs_rect_workspace_bytes(int B, int C, int H1, int W1, int H2, int W2, int precision);
+int b200corr_allpairs_pyramid_rect(const float *f1, const float *f2, float *const *h_levels,
+                                   int num_levels, int B, int C, int H1, int W1, int H2, int W2, float scale,
+                                   int precision, void *workspace, size_t workspace_bytes, void *stream);
+
 /* out[B, num_levels*(2r+1)^2, H, W]; coords[B, 2, H, W] (channel 0 = x).  Channel index
  * l*(2r+1)^2 + i*(2r+1) + j, i = x-offset index, j = y-offset index (corr.py:80-86). */
 int b200corr_lookup_forward(const float *const *h_levels, int num_levels, const float *coords,
                             float *out, int B, int H, int W, int radius, int mode, void *stream);
+
+/* Same for a run of pyramid levels that does not start at level 0: list entry i is pyramid level
+ * first_level + i, i.e. has extent (H, W) >> (first_level + i) and samples at coords / 2^(first_level + i);
+ * out[B, num_levels*(2r+1)^2, H, W] holds just these levels. */
+int b200corr_lookup_forward_from(const float *const *h_levels, int num_levels, int first_level,
+                                 const float *coords, float *out, int B, int H, int W, int radius, int mode,
+                                 void *stream);
 
 /* Accumulates (+=) d(out)/d(level l) into h_grad_levels[l] (caller zero-initialises once per
  * CorrBlock; several lookups of the same block accumulate).  Coordinates get no gradient

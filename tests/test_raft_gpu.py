@@ -305,6 +305,30 @@ def test_alt_corr_vs_oracle_and_corrblock(path):
     assert _maxabs(alt.cpu().numpy() - z["out"]) <= 1e-4 * _maxabs(z["out"])
 
 
+@pytest.mark.parametrize("shape,dense_from", [((2, 64, 24, 48), 1), ((1, 32, 16, 32), 1), ((1, 16, 8, 16), 0),
+                                              ((1, 32, 16, 20), 3)], ids=str)
+def test_alt_corr_hybrid_equals_alt_kernels(shape, dense_from):
+    """AlternateCorrBlock serves the coarse levels (small key maps) from dense split-TF32 volumes + the
+    lookup kernel; the result must equal the pure alt_cuda_corr structure (dense_max_keys=0) and CorrBlock."""
+    from understanding_flow_robustness_b200 import AlternateCorrBlock, CorrBlock, coords_grid
+    B, C, H, W = shape
+    torch.manual_seed(H + W)
+    f1 = torch.randn(B, C, H, W, device="cuda")
+    f2 = torch.randn(B, C, H, W, device="cuda")
+    for sigma in (2.0, 30.0):
+        c = coords_grid(B, H, W, "cuda") + sigma * torch.randn(B, 2, H, W, device="cuda")
+        with torch.no_grad():
+            pure = AlternateCorrBlock(f1, f2, 3, 3, dense_max_keys=0)
+            hyb = AlternateCorrBlock(f1, f2, 3, 3, dense_max_keys=400)
+            assert pure._dense_from == 3 and hyb._dense_from == dense_from   # (16x20: level widths 10, 5 -> not applicable)
+            a, b = pure(c), hyb(c)
+            ref = CorrBlock(f1, f2, 3, 3, precision="fp32", lookup_mode="direct")(c)
+        s = float(a.abs().max())
+        assert a.shape == b.shape == ref.shape
+        assert float((a - b).abs().max()) <= 1e-5 * s
+        assert float((b - ref).abs().max()) <= 1e-4 * s
+
+
 def test_alt_corr_multi_n_and_autograd():
     from oracle import raft_oracle
     from understanding_flow_robustness_b200 import AlternateCorrBlock, alt_cuda_corr, coords_grid

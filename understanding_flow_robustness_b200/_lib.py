@@ -23,8 +23,13 @@ PROTOTYPES = {
     "b200corr_allpairs_workspace_bytes": (c_size_t, [c_int] * 5),
     "b200corr_allpairs_pyramid": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int,
                                           c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "b200corr_allpairs_rect_workspace_bytes": (c_size_t, [c_int] * 7),
+    "b200corr_allpairs_pyramid_rect": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int,
+                                               c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "b200corr_lookup_forward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_int,
                                         c_int, c_int, c_int, c_void_p]),
+    "b200corr_lookup_forward_from": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                             c_int, c_int, c_int, c_void_p]),
     "b200corr_lookup_backward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_int,
                                          c_int, c_int, c_int, c_void_p]),
     "b200corr_pyramid_backward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),

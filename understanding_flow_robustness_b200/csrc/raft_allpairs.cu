@@ -101,7 +101,7 @@ struct Cfg {
 };
 
 struct Params {
-  int B, HW, H, W, KB;       // KB = Cp / 32
+  int B, HW, H, W, KB;       // HW = query pixels (rows of the volume), H x W = key map; KB = Cp / 32
   int passes;                // 1: TF32.  3: TF32x3 -- the k loop runs over lo*hi, hi*lo, hi*hi (K-extended GEMM)
   int MT, NTY, NTX;          // tile counts (MT counts 128*CTAS-row blocks)
   float scale;
@@ -509,23 +509,35 @@ int launch_pool(const float *in, float *out, long long Q, int Hi, int Wi, cudaSt
 
 extern "C" {
 
-size_t b200corr_allpairs_workspace_bytes(int B, int C, int H, int W, int precision) {
+size_t b200corr_allpairs_rect_workspace_bytes(int B, int C, int H1, int W1, int H2, int W2, int precision) {
   if (precision == B200CORR_PREC_FP32) return 0;
   const size_t Cp = (size_t)(C + 31) / 32 * 32;
-  return (precision == B200CORR_PREC_TF32X3 ? 4 : 2) * (size_t)B * H * W * Cp * sizeof(float);
+  return (precision == B200CORR_PREC_TF32X3 ? 2 : 1) * (size_t)B * ((size_t)H1 * W1 + (size_t)H2 * W2) * Cp * sizeof(float);
+}
+
+size_t b200corr_allpairs_workspace_bytes(int B, int C, int H, int W, int precision) {
+  return b200corr_allpairs_rect_workspace_bytes(B, C, H, W, H, W, precision);
 }
 
 int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_levels,
                               int num_levels, int B, int C, int H, int W, float scale,
                               int precision, void *workspace, size_t workspace_bytes, void *stream_) {
+  return b200corr_allpairs_pyramid_rect(f1, f2, h_levels, num_levels, B, C, H, W, H, W, scale, precision, workspace,
+                                        workspace_bytes, stream_);
+}
+
+int b200corr_allpairs_pyramid_rect(const float *f1, const float *f2, float *const *h_levels,
+                                   int num_levels, int B, int C, int H1, int W1, int H, int W, float scale,
+                                   int precision, void *workspace, size_t workspace_bytes, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK(num_levels >= 1 && num_levels <= 8, "allpairs_pyramid: num_levels must be in [1, 8]");
-  B200_CHECK(B >= 0 && C >= 1 && H >= 1 && W >= 1, "allpairs_pyramid: bad sizes");
+  B200_CHECK(B >= 0 && C >= 1 && H >= 1 && W >= 1 && H1 >= 1 && W1 >= 1, "allpairs_pyramid: bad sizes");
   B200_CHECK(precision == B200CORR_PREC_TF32 || precision == B200CORR_PREC_TF32X3 || precision == B200CORR_PREC_FP32,
              "allpairs_pyramid: precision %d not available (TF32 = 0, TF32X3 = 1, FP32 = 2)", precision);
   if (B == 0) return 0;
   B200_CHECK(f1 && f2 && h_levels && h_levels[0], "allpairs_pyramid: null pointer");
-  const int HW = H * W;
+  const int HW = H * W;        // key pixels (the maps of f2 and of every level)
+  const int HWq = H1 * W1;     // query pixels (f1)
   int LH[8], LW[8];
   LH[0] = H; LW[0] = W;
   for (int l = 1; l < num_levels; ++l) {
@@ -533,10 +545,11 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
     LW[l] = LW[l - 1] / 2;
     B200_CHECK(h_levels[l] || LH[l] * LW[l] == 0, "allpairs_pyramid: null level %d", l);
   }
-  const long long Q = (long long)B * HW;
+  const long long Q = (long long)B * HWq;
   int first_unpooled = 1;  // first level that still has to be produced by the pooling kernel
 
   if (precision == B200CORR_PREC_FP32 || W % 4 != 0) {
+    B200_CHECK(HWq == HW, "allpairs_pyramid_rect: the exact fp32 / W %% 4 != 0 path needs equal map sizes");
     dim3 grid((HW + 63) / 64, (HW + 63) / 64, B);
     allpairs_simt_kernel<<<grid, 256, 0, stream>>>(f1, f2, h_levels[0], C, HW, scale);
     B200_LAUNCH_OK("allpairs_simt_kernel");
@@ -550,18 +563,18 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
       if (b200::num_sms() % 2) ctas = 1;
     }
     const bool x3 = precision == B200CORR_PREC_TF32X3;
-    const size_t need = (x3 ? 4 : 2) * (size_t)B * HW * Cp * sizeof(float);
+    const size_t nfeat1 = (size_t)B * HWq * Cp, nfeat2 = (size_t)B * HW * Cp;
+    const size_t need = (x3 ? 2 : 1) * (nfeat1 + nfeat2) * sizeof(float);
     B200_CHECK(workspace && workspace_bytes >= need,
                "allpairs_pyramid: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     B200_CHECK(((uintptr_t)workspace & 127) == 0 && ((uintptr_t)h_levels[0] & 15) == 0,
                "allpairs_pyramid: workspace must be 128-byte and level 0 16-byte aligned");
-    const size_t nfeat = (size_t)B * HW * Cp;
-    float *f1t = (float *)workspace, *f2t = f1t + nfeat;
-    float *f1lo = x3 ? f2t + nfeat : nullptr, *f2lo = x3 ? f1lo + nfeat : nullptr;
-    dim3 pgrid((HW + 31) / 32, Cp / 32, B);
-    prep_kmajor_tf32_kernel<<<pgrid, 256, 0, stream>>>(f1, f1t, f1lo, C, Cp, HW);
+    float *f1t = (float *)workspace, *f2t = f1t + nfeat1;
+    float *f1lo = x3 ? f2t + nfeat2 : nullptr, *f2lo = x3 ? f1lo + nfeat1 : nullptr;
+    dim3 pgrid1((HWq + 31) / 32, Cp / 32, B), pgrid2((HW + 31) / 32, Cp / 32, B);
+    prep_kmajor_tf32_kernel<<<pgrid1, 256, 0, stream>>>(f1, f1t, f1lo, C, Cp, HWq);
     B200_LAUNCH_OK("prep_kmajor_tf32_kernel");
-    prep_kmajor_tf32_kernel<<<pgrid, 256, 0, stream>>>(f2, f2t, f2lo, C, Cp, HW);
+    prep_kmajor_tf32_kernel<<<pgrid2, 256, 0, stream>>>(f2, f2t, f2lo, C, Cp, HW);
     B200_LAUNCH_OK("prep_kmajor_tf32_kernel");
 
     CUtensorMap mapA, mapB, mapAlo, mapBlo;
@@ -569,8 +582,8 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
       CUtensorMap &mapA_ = which ? mapAlo : mapA, &mapB_ = which ? mapBlo : mapB;
       const float *f1t_ = which ? f1lo : f1t, *f2t_ = which ? f2lo : f2t;
     {
-      const uint64_t dims[3] = {(uint64_t)Cp, (uint64_t)HW, (uint64_t)B};
-      const uint64_t str[3] = {4, (uint64_t)Cp * 4, (uint64_t)HW * Cp * 4};
+      const uint64_t dims[3] = {(uint64_t)Cp, (uint64_t)HWq, (uint64_t)B};
+      const uint64_t str[3] = {4, (uint64_t)Cp * 4, (uint64_t)HWq * Cp * 4};
       const uint32_t box[3] = {tc::BK, tc::BM, 1};
       if (int e = b200::make_tensor_map(&mapA_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, f1t_, dims, str, box,
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
@@ -587,9 +600,9 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
     }
     if (!x3) { mapAlo = mapA; mapBlo = mapB; }
     tc::Params p;
-    p.B = B; p.HW = HW; p.H = H; p.W = W; p.KB = Cp / 32;
+    p.B = B; p.HW = HWq; p.H = H; p.W = W; p.KB = Cp / 32;
     p.passes = x3 ? 3 : 1;
-    p.MT = (HW + tc::BM * ctas - 1) / (tc::BM * ctas);
+    p.MT = (HWq + tc::BM * ctas - 1) / (tc::BM * ctas);
     p.NTY = (H + tc::PH - 1) / tc::PH;
     p.NTX = (W + tc::PW - 1) / tc::PW;
     p.scale = scale;

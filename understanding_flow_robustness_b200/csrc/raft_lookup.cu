@@ -45,6 +45,7 @@ struct LookupParams {
   int LH[kMaxLevels], LW[kMaxLevels];
   int path[kMaxLevels];  // access flavour per level (sector / 16-byte / scalar), from width and alignment
   int num_levels, B, HW, radius, mode;
+  int first_level;   // pyramid level of list entry 0: entry i has extent (H, W) >> (first_level + i), coordinate scale 2^-(first_level + i)
 };
 
 template <int R>
@@ -220,8 +221,9 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
     cy = coords[((size_t)b * 2 + 1) * p.HW + q];
   }
   int xlo, xhi;
-  a.ox = window_origin<R>(cx, lvl, xlo, xhi);
-  a.oy = window_origin<R>(cy, lvl, a.ylo, a.yhi);
+  const int slvl = lvl + p.first_level;   // coordinate scale of this level
+  a.ox = window_origin<R>(cx, slvl, xlo, xhi);
+  a.oy = window_origin<R>(cy, slvl, a.ylo, a.yhi);
   // staged column of window column 0, and the staged columns the taps touch
   const int shift = path == PATH_SCALAR ? 0 : (a.ox & 3);
   a.clo = shift + xlo; a.chi = shift + xhi;
@@ -239,7 +241,7 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
     const bool isy = e >= N;
     int rel;
     float frac;
-    one_tap<R>(isy ? cy : cx, lvl, isy ? e - N : e, isy ? smy : smx, isy ? ismy : ismx, mode, isy ? a.oy : a.ox, rel, frac);
+    one_tap<R>(isy ? cy : cx, slvl, isy ? e - N : e, isy ? smy : smx, isy ? ismy : ismx, mode, isy ? a.oy : a.ox, rel, frac);
     // a tap outside the staged rows / columns cannot happen (window_origin); drop it if it does
     const int lo = isy ? a.ylo : xlo, hi = isy ? a.yhi : xhi;
     if (rel >= 0 && (rel < lo || rel + 1 > hi)) { rel = -1; frac = 0.f; }
@@ -379,7 +381,8 @@ lookup_bwd_kernel(const LookupParams p, const float *__restrict__ coords,
     cy = coords[((size_t)b * 2 + 1) * p.HW + q];
   }
   int xlo, xhi, ylo, yhi;
-  const int ox = window_origin<R>(cx, lvl, xlo, xhi), oy = window_origin<R>(cy, lvl, ylo, yhi);
+  const int slvl = lvl + p.first_level;   // coordinate scale of this level
+  const int ox = window_origin<R>(cx, slvl, xlo, xhi), oy = window_origin<R>(cy, slvl, ylo, yhi);
   const int shift = path == PATH_SCALAR ? 0 : (ox & 3);
   const float smx = (float)(LW - 1), smy = (float)(LH - 1);
   const float ismx = __frcp_rn(smx), ismy = __frcp_rn(smy);
@@ -388,7 +391,7 @@ lookup_bwd_kernel(const LookupParams p, const float *__restrict__ coords,
     const bool isy = e >= N;
     int rel;
     float frac;
-    one_tap<R>(isy ? cy : cx, lvl, isy ? e - N : e, isy ? smy : smx, isy ? ismy : ismx, mode, isy ? oy : ox, rel, frac);
+    one_tap<R>(isy ? cy : cx, slvl, isy ? e - N : e, isy ? smy : smx, isy ? ismy : ismx, mode, isy ? oy : ox, rel, frac);
     const int lo = isy ? ylo : xlo, hi = isy ? yhi : xhi;
     if (rel >= 0 && (rel < lo || rel + 1 > hi)) { rel = -1; frac = 0.f; }   // same rule as the forward
     tab_r[e][lane] = rel;
@@ -507,14 +510,15 @@ pool_bwd_kernel(float *__restrict__ fine, const float *__restrict__ coarse, long
 }
 
 int fill_params(LookupParams &p, const float *const *lv, float *const *glv, int num_levels, int B,
-                int H, int W, int radius, int mode, const char *who) {
+                int H, int W, int radius, int mode, const char *who, int first_level = 0) {
   B200_CHECK(num_levels >= 1 && num_levels <= kMaxLevels, "%s: num_levels must be in [1, %d]", who,
              kMaxLevels);
   B200_CHECK(radius >= 1 && radius <= 4, "%s: radius %d not instantiated (1..4)", who, radius);
   B200_CHECK(mode == B200CORR_LOOKUP_GRIDSAMPLE || mode == B200CORR_LOOKUP_DIRECT, "%s: bad mode", who);
   B200_CHECK(B >= 0 && H >= 1 && W >= 1, "%s: bad sizes", who);
-  p.num_levels = num_levels; p.B = B; p.HW = H * W; p.radius = radius; p.mode = mode;
-  int h = H, w = W;
+  B200_CHECK(first_level >= 0 && first_level + num_levels <= 16, "%s: bad first_level %d", who, first_level);
+  p.num_levels = num_levels; p.B = B; p.HW = H * W; p.radius = radius; p.mode = mode; p.first_level = first_level;
+  int h = H >> first_level, w = W >> first_level;
   for (int l = 0; l < kMaxLevels; ++l) {
     p.lvl[l] = nullptr; p.glvl[l] = nullptr; p.LH[l] = 0; p.LW[l] = 0; p.path[l] = 0;
     if (l < num_levels) {
@@ -534,10 +538,16 @@ extern "C" {
 
 int b200corr_lookup_forward(const float *const *h_levels, int num_levels, const float *coords,
                             float *out, int B, int H, int W, int radius, int mode, void *stream_) {
+  return b200corr_lookup_forward_from(h_levels, num_levels, 0, coords, out, B, H, W, radius, mode, stream_);
+}
+
+int b200corr_lookup_forward_from(const float *const *h_levels, int num_levels, int first_level,
+                                 const float *coords, float *out, int B, int H, int W, int radius, int mode,
+                                 void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LookupParams p;
   if (B == 0) return 0;   // empty tensors have no storage: nothing to validate, nothing to do
-  if (int e = fill_params(p, h_levels, nullptr, num_levels, B, H, W, radius, mode, "lookup_forward")) return e;
+  if (int e = fill_params(p, h_levels, nullptr, num_levels, B, H, W, radius, mode, "lookup_forward", first_level)) return e;
   B200_CHECK(coords && out, "lookup_forward: null pointer");
   for (int l = 0; l < num_levels; ++l) {
     const uintptr_t a = (uintptr_t)p.lvl[l];

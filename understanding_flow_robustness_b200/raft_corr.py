@@ -96,18 +96,43 @@ def allpairs_pyramid(fmap1, fmap2, num_levels=4, precision="tf32"):
     return levels
 
 
-def lookup_forward(levels, coords, radius, H, W, mode="grid_sample"):
+def lookup_forward(levels, coords, radius, H, W, mode="grid_sample", first_level=0):
+    """`levels[i]` is pyramid level first_level + i: extent (H, W) >> (first_level + i), sampled at
+    coords / 2^(first_level + i)."""
     coords = coords.contiguous()
     _require_cuda_f32("lookup_forward", coords, *levels)
     B = coords.shape[0]
     n = (2 * radius + 1) ** 2
     out = torch.empty((B, len(levels) * n, H, W), dtype=torch.float32, device=coords.device)
     with torch.cuda.device(coords.device):
-        code = _lib.lib().b200corr_lookup_forward(_lib.ptr_array(levels), len(levels), _lib.ptr(coords),
-                                                  _lib.ptr(out), B, H, W, radius, LOOKUP_MODES[mode],
-                                                  _lib.current_stream(coords.device))
-    _lib.check(code, "b200corr_lookup_forward")
+        code = _lib.lib().b200corr_lookup_forward_from(_lib.ptr_array(levels), len(levels), first_level,
+                                                       _lib.ptr(coords), _lib.ptr(out), B, H, W, radius,
+                                                       LOOKUP_MODES[mode], _lib.current_stream(coords.device))
+    _lib.check(code, "b200corr_lookup_forward_from")
     return out
+
+
+def allpairs_volume_rect(fmap1, fmap2, precision="tf32x3"):
+    """(B*H1*W1, 1, H2, W2) volume of f1 (queries) against a key map of another size (AlternateCorrBlock's
+    pooled f2): vol[b,p1,y,x] = f1[b,:,p1] . f2[b,:,y,x] / sqrt(C).  Tensor-core precisions, W2 % 4 == 0."""
+    fmap1 = fmap1.contiguous()
+    fmap2 = fmap2.contiguous()
+    _require_cuda_f32("allpairs_volume_rect", fmap1, fmap2)
+    B, C, H1, W1 = fmap1.shape
+    H2, W2 = fmap2.shape[-2:]
+    if fmap2.shape[:2] != fmap1.shape[:2] or W2 % 4 != 0 or precision == "fp32":
+        raise RuntimeError("allpairs_volume_rect: need equal batch / channels, W2 % 4 == 0 and a tensor-core precision")
+    prec = PRECISIONS[precision]
+    L = _lib.lib()
+    vol = torch.empty((B * H1 * W1, 1, H2, W2), dtype=torch.float32, device=fmap1.device)
+    nbytes = L.b200corr_allpairs_rect_workspace_bytes(B, C, H1, W1, H2, W2, prec)
+    ws = torch.empty((max(nbytes, 1) + 127) // 128 * 32, dtype=torch.float32, device=fmap1.device)
+    with torch.cuda.device(fmap1.device):
+        code = L.b200corr_allpairs_pyramid_rect(_lib.ptr(fmap1), _lib.ptr(fmap2), _lib.ptr_array([vol]), 1, B, C, H1, W1,
+                                                H2, W2, 1.0 / math.sqrt(C), prec, _lib.ptr(ws), nbytes,
+                                                _lib.current_stream(fmap1.device))
+    _lib.check(code, "b200corr_allpairs_pyramid_rect")
+    return vol
 
 
 def lookup_backward(grad_levels, coords, grad_out, radius, H, W, mode="grid_sample"):
@@ -318,11 +343,19 @@ class CorrBlock:
 
 
 class AlternateCorrBlock:
-    """models/raft/corr.py:109-137.  The NHWC copies are made once here instead of on every call."""
+    """models/raft/corr.py:109-137.  The NHWC copies are made once here instead of on every call.
 
-    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+    The block exists to avoid the (H*W)^2 volume.  From the level on where the pooled key map has at most
+    `dense_max_keys` pixels (levels >= 2 at 48x160: 1/16 + 1/64 of the full volume) a 10x10 window covers
+    most of the map anyway, so those levels are served from a small dense volume built once on the tensor
+    cores (split TF32: fp32-level accuracy) and the bilinear lookup kernel; the fine levels keep the
+    on-the-fly alt_cuda_corr kernel.  Same values; inference only (with autograd every level uses
+    alt_cuda_corr, which carries the gradient).  dense_max_keys=0 restores the reference's structure."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, dense_max_keys=1024):
         self.num_levels = num_levels
         self.radius = radius
+        needs_grad = torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad)
         self.pyramid = [(fmap1, fmap2)]
         for _ in range(self.num_levels):
             fmap1 = F.avg_pool2d(fmap1, 2, stride=2)
@@ -330,16 +363,38 @@ class AlternateCorrBlock:
             self.pyramid.append((fmap1, fmap2))
         self._f1 = self.pyramid[0][0].permute(0, 2, 3, 1).contiguous().float()
         self._f2 = [self.pyramid[i][1].permute(0, 2, 3, 1).contiguous().float() for i in range(num_levels)]
+        # first level served from a dense volume (every coarser level is smaller still)
+        self._dense_from = num_levels
+        self._dense = []
+        B = self._f1.shape[0]
+        if not needs_grad and dense_max_keys > 0 and B > 0 and 1 <= radius <= 4:
+            for i in range(num_levels):
+                h, w = self.pyramid[i][1].shape[-2:]
+                if h * w <= dense_max_keys and all(self.pyramid[j][1].shape[-1] % 4 == 0 and
+                                                   min(self.pyramid[j][1].shape[-2:]) >= 1
+                                                   for j in range(i, num_levels)):
+                    self._dense_from = i
+                    break
+            f1 = self.pyramid[0][0].float()
+            self._dense = [allpairs_volume_rect(f1, self.pyramid[j][1].float()) for j in range(self._dense_from, num_levels)]
 
     def __call__(self, coords):
-        coords = coords.permute(0, 2, 3, 1)
-        B, H, W, _ = coords.shape
+        coords_nhwc = coords.permute(0, 2, 3, 1)
+        B, H, W, _ = coords_nhwc.shape
         dim = self.pyramid[0][0].shape[1]
+        n = (2 * self.radius + 1) ** 2
         corr_list = []
-        for i in range(self.num_levels):
-            coords_i = (coords / 2 ** i).reshape(B, 1, H, W, 2).contiguous().float().detach()
+        for i in range(self._dense_from):
+            coords_i = (coords_nhwc / 2 ** i).reshape(B, 1, H, W, 2).contiguous().float().detach()
             corr = _AltCorrFunction.apply(self._f1, self._f2[i], coords_i, self.radius)
             corr_list.append(corr.squeeze(1))
-        corr = torch.stack(corr_list, dim=1)
-        corr = corr.reshape(B, self.num_levels * (2 * self.radius + 1) ** 2, H, W)   # (-1 is ambiguous for B = 0)
-        return corr / math.sqrt(dim)
+        parts = []
+        if corr_list:
+            parts.append(torch.stack(corr_list, dim=1).reshape(B, len(corr_list) * n, H, W) / math.sqrt(dim))
+        if self._dense:
+            # the dense volumes already carry the 1/sqrt(C) factor; "direct" = alt_cuda_corr's coordinates
+            parts.append(lookup_forward(self._dense, coords.detach().float(), self.radius, H, W, "direct",
+                                        first_level=self._dense_from))
+        if len(parts) == 1:
+            return parts[0]
+        return torch.cat(parts, dim=1) if parts else coords.new_zeros((B, 0, H, W))
