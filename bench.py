@@ -433,6 +433,10 @@ def main():
         line["attack"] = attack_res
     if not args.no_raft:
         line["raft"] = raft_bench(dev)
+        try:
+            line["merge_block"] = merge_bench(dev)
+        except Exception as e:
+            line["merge_block"] = {"error": f"{type(e).__name__}: {e}"}
     if not args.no_cpu_baseline:
         try:
             _, _, cb = reference_cpu_pairs_per_s(steps=3, warmup=1, budget_s=3.0)
@@ -512,6 +516,52 @@ def attack_bench(dev, rank, world, global_batch):
             "allreduce_bytes": int(patch.numel() * 4 + 4),
             "flownetc_fwd_bwd_pairs_per_s_per_gpu": net_pairs_per_s,
             "flownetc_config": "BASELINE config 2: FlowNetC harness random init, forward+backward, 384x1280, batch 8, 1 GPU"}
+
+
+def merge_bench(dev):
+    """the FlowNetC merge block (correlate -> /C -> LeakyReLU -> cat, forward + backward
+    w.r.t. both feature maps and the redir map) as one fused operator vs the same chain of torch ops on this
+    package's unfused sampler.  Feature shape of BASELINE config 2."""
+    import torch
+    import torch.nn.functional as F
+
+    from understanding_flow_robustness_b200 import correlate_merge, spatial_correlation_sample
+    B, C, H, W = CFG["B"], CFG["C"], CFG["H"], CFG["W"]
+    torch.manual_seed(0)
+    a = torch.randn(B, C, H, W, device=dev, requires_grad=True)
+    b = torch.randn(B, C, H, W, device=dev, requires_grad=True)
+    r = torch.randn(B, 32, H, W, device=dev, requires_grad=True)
+    g = torch.randn(B, 32 + 441, H, W, device=dev)
+
+    def fused():
+        correlate_merge(a, b, r, 21, 2, 0.1).backward(g)
+
+    def unfused():
+        out = spatial_correlation_sample(a, b, kernel_size=1, patch_size=21, stride=1, padding=0, dilation_patch=2)
+        out = out.view(B, 441, H, W) / a.size(1)
+        torch.cat((r, F.leaky_relu(out, 0.1)), 1).backward(g)
+
+    def timeit(fn, n=20):
+        for _ in range(5):
+            fn()
+            a.grad = b.grad = r.grad = None
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+            a.grad = b.grad = r.grad = None
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    tf, tu = timeit(fused), timeit(unfused)
+    cv = B * 441 * H * W * 4
+    return {"metric": "FlowNetC merge block fwd+bwd pairs/s", "fused_ms": tf, "unfused_ms": tu,
+            "fused_pairs_per_s": B / (tf * 1e-3), "unfused_pairs_per_s": B / (tu * 1e-3),
+            "config": f"features ({B},{C},{H},{W}), redir 32 channels, LeakyReLU 0.1; eager autograd calls, CUDA events",
+            "cost_volume_passes": {"fused": "1 write (fwd) + 2 reads + 1 write + 2 reads (bwd)",
+                                   "unfused": "7 (fwd) + 7 + 2 reads (bwd)", "bytes_per_pass": cv}}
 
 
 def raft_bench(dev):

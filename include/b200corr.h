@@ -115,6 +115,27 @@ int b200corr_sampler_uses_fast_path(int B, int C, int H, int W, int kH, int kW, 
                                     int dilation_patchH, int dilation_patchW, int dH, int dW,
                                     int dtype, int backward);
 
+/* ---------------------------------------------------------------- fused FlowNetC merge block
+ * (SURVEY.md section 8(f) row 2).  Replaces, at the FlowNetC call sites, the chain
+ *   correlate(a, b) = spatial_correlation_sample(a, b, 1, patch, 1, 0, dilation_patch).view(B, P*P, H, W) / C
+ *                                                                     models/submodules.py:124-138
+ *   LeakyReLU(slope) ; torch.cat((conv_redir(a), out_corr), 1)       models/FlowNetC.py:133-147
+ * by one kernel that writes leaky_relu(corr / C) into channels [c_off, c_off + P*P) of the caller's
+ * (B, c_total, H, W) concat tensor `merged` (the other channels are not touched).  kernel 1, stride 1,
+ * padding 0, fp32; only shapes b200corr_merge_supported() accepts (the register-blocked kernels). */
+int b200corr_merge_supported(int B, int C, int H, int W, int patch, int dilation_patch);
+int b200corr_merge_forward(const float *in1, const float *in2, float *merged, int B, int C, int H, int W,
+                           int patch, int dilation_patch, int c_total, int c_off, float slope, void *stream);
+
+/* Gradients w.r.t. in1 / in2 from the gradient of the concat tensor (same (B, c_total, H, W) layout) and
+ * the forward's `merged` (its sign is the LeakyReLU mask).  grad_scratch: b200corr_merge_backward_scratch_bytes()
+ * bytes of device memory (the masked, scaled, gathered slice); plan_workspace as in b200corr_sampler_backward. */
+size_t b200corr_merge_backward_scratch_bytes(int B, int H, int W, int patch);
+int b200corr_merge_backward(const float *in1, const float *in2, const float *merged, const float *grad_merged,
+                            float *grad_in1, float *grad_in2, void *grad_scratch, void *plan_workspace,
+                            size_t plan_workspace_bytes, int B, int C, int H, int W, int patch, int dilation_patch,
+                            int c_total, int c_off, float slope, void *stream);
+
 /* ---------------------------------------------------------------- RAFT CorrBlock */
 
 /* Level l has shape (B*H*W, 1, H_l, W_l), H_0 = H, H_{l+1} = H_l / 2 (floor), same for W. */

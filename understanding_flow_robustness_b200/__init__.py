@@ -4,6 +4,8 @@ Public surface (same names / signatures as the reference's operator API):
   spatial_correlation_sample, SpatialCorrelationSampler, SpatialCorrelationSamplerFunction
       <- models/Pytorch-Correlation-extension/Correlation_Module/spatial_correlation_sampler/
   CorrBlock, AlternateCorrBlock, alt_cuda_corr            <- models/raft/corr.py, models/alt_cuda_corr/
+  correlate_merge   correlate() -> LeakyReLU -> cat of the FlowNetC merge block as one kernel
+      <- models/submodules.py:124-138 + models/FlowNetC.py:133-147
   install_reference_shims()  registers `spatial_correlation_sampler`, `spatial_correlation_sampler_backend`
       and `alt_cuda_corr` in sys.modules so the reference's model files import this implementation.
 
@@ -24,6 +26,10 @@ def __getattr__(name):
         from . import raft_corr
 
         return getattr(raft_corr, name)
+    if name in ("correlate_merge", "CorrelateMergeFunction"):
+        from . import merge_block
+
+        return getattr(merge_block, name)
     if name == "install_reference_shims":
         from .shims import install_reference_shims
 

@@ -20,6 +20,10 @@ PROTOTYPES = {
     "b200corr_sampler_backward": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 17 + [c_void_p]),
     "b200corr_sampler_uses_fast_path": (c_int, [c_int] * 18),
     "b200corr_sampler_backward_plan": (c_int, [c_int] * 17 + [c_void_p, c_size_t]),
+    "b200corr_merge_supported": (c_int, [c_int] * 6),
+    "b200corr_merge_forward": (c_int, [c_void_p] * 3 + [c_int] * 8 + [c_float, c_void_p]),
+    "b200corr_merge_backward_scratch_bytes": (c_size_t, [c_int] * 4),
+    "b200corr_merge_backward": (c_int, [c_void_p] * 8 + [c_size_t] + [c_int] * 8 + [c_float, c_void_p]),
     "b200corr_allpairs_workspace_bytes": (c_size_t, [c_int] * 5),
     "b200corr_allpairs_pyramid": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int,
                                           c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),

@@ -69,6 +69,8 @@ int sampler_generic_backward(const void *in1, const void *in2, const void *gout,
 bool sampler_fast_applicable(int B, int C, int H, int W, const int *q, int dtype, int backward);
 int sampler_fast_forward(const float *in1, const float *in2, float *out, int B, int C, int H, int W,
                          const int *q, cudaStream_t stream);
+int sampler_fast_forward_merge(const float *in1, const float *in2, float *out, int B, int C, int H, int W,
+                               const int *q, long long out_bstride, float slope, cudaStream_t stream);
 int sampler_fast_backward(const float *in1, const float *in2, const float *gout, float *gin1,
                           float *gin2, int B, int C, int H, int W, const int *q, const int *plan,
                           cudaStream_t stream);
@@ -108,6 +110,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe of a phase (try_wait may suspend the thread for a while; test_wait never does)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)

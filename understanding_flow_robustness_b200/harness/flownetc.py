@@ -43,10 +43,11 @@ class FlowNetCHarness(nn.Module):
              ("conv5", 512, 512, 3, 2), ("conv5_1", 512, 512, 3, 1), ("conv6", 512, 1024, 3, 2),
              ("conv6_1", 1024, 1024, 3, 1)]
 
-    def __init__(self, div_flow=20.0, corr_fn=correlate):
+    def __init__(self, div_flow=20.0, corr_fn=correlate, fused_merge=False):
         super().__init__()
         self.div_flow = div_flow
         self.corr_fn = corr_fn
+        self.fused_merge = fused_merge   # correlate -> LeakyReLU -> cat as one kernel (merge_block.correlate_merge)
         for name, cin, cout, k, s in self.ENCODER + self.TRUNK:
             setattr(self, name, _conv(cin, cout, k, s))
         self.conv_redir = _conv(256, 32, 1, 1)
@@ -70,8 +71,13 @@ class FlowNetCHarness(nn.Module):
     def forward(self, img1, img2):
         c2a, c3a = self.features(img1)
         _, c3b = self.features(img2)
-        corr = F.leaky_relu(self.corr_fn(c3a, c3b), 0.1)
-        x3 = self.conv3_1(torch.cat((self.conv_redir(c3a), corr), 1))
+        if self.fused_merge:
+            from ..merge_block import correlate_merge
+
+            x3 = self.conv3_1(correlate_merge(c3a, c3b, self.conv_redir(c3a), 21, 2, 0.1))
+        else:
+            corr = F.leaky_relu(self.corr_fn(c3a, c3b), 0.1)
+            x3 = self.conv3_1(torch.cat((self.conv_redir(c3a), corr), 1))
         x4 = self.conv4_1(self.conv4(x3))
         x5 = self.conv5_1(self.conv5(x4))
         x6 = self.conv6_1(self.conv6(x5))
