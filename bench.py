@@ -344,6 +344,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    # FP32 FFMA peak (the roofline denominator), measured right behind the timed region: same clocks,
+    # same power / thermal state as the kernels it is compared with (measured after the attack bench it
+    # read 65.8 instead of 72.6 TFLOP/s on one box: the power cap of a GPU that had just run the conv stack)
+    import ctypes
+    pk = ctypes.c_float()
+    _lib.check(L.b200corr_measure_fp32_peak(4000, ctypes.byref(pk), _lib.current_stream(dev)), "fp32 peak")
+    peak = float(pk.value)
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
 
@@ -397,10 +404,6 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (sampler_bwd_kernel: two launches per step)
-    import ctypes
-    pk = ctypes.c_float()
-    _lib.check(L.b200corr_measure_fp32_peak(4000, ctypes.byref(pk), _lib.current_stream(dev)), "fp32 peak")
-    peak = float(pk.value)
     macs = inbounds_macs_per_pair(C, H, W, P, CFG["dilation_patch"])
     flop_launch = 2.0 * macs * B                      # one gradient (or the forward): in-bounds FLOPs
     bwd_launch_ms = bwd_ms / 2.0
