@@ -40,7 +40,8 @@ def test_host_only_entry_points(lib):
     f = lib.b200corr_sampler_uses_fast_path
     assert f(8, 256, 48, 160, 1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1, 0, 0) == 1
     assert f(8, 256, 48, 160, 1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1, 0, 1) == 1
-    assert f(8, 196, 48, 160, 1, 1, 9, 9, 0, 0, 1, 1, 1, 1, 1, 1, 0, 1) == 0   # C % 32 != 0 backward
+    assert f(8, 196, 6, 20, 1, 1, 9, 9, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0) == 1    # PWC-Net level 6: channel tail via 4-D TMA maps
+    assert f(8, 196, 6, 20, 1, 1, 9, 9, 0, 0, 1, 1, 1, 1, 1, 1, 0, 1) == 1
     assert f(8, 96, 48, 160, 1, 1, 9, 9, 0, 0, 1, 1, 1, 1, 1, 1, 0, 1) == 1
     assert f(1, 10, 10, 10, 3, 3, 3, 3, 5, 5, 2, 2, 2, 2, 2, 2, 1, 0) == 0
     assert f(1, 8, 12, 13, 1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1, 0, 0) == 0    # W % 4 != 0

@@ -81,6 +81,10 @@ FAST_CASES = [
     (2, 96, 12, 40, 9, 1),       # PWC-Net level: C % 32 == 0 backward (2 channels per thread)
     (1, 32, 24, 80, 9, 1),
     (1, 64, 13, 24, 21, 2),      # patch 21 with the 32-channel unit
+    (2, 196, 6, 20, 9, 1),       # PWC-Net level 6: C % 8 != 0 -> 4-D tensor maps, zero-filled channel tail
+    (3, 5, 9, 12, 9, 1),         # fewer channels than one chunk, several samples (a 3-D map would read the next sample)
+    (2, 37, 10, 16, 21, 2),      # odd channel count on the patch-21 kernels
+    (2, 130, 7, 12, 21, 2),      # C % 128 != 0 and C % 32 != 0: 32-channel backward units with a tail
 ]
 
 

@@ -72,7 +72,7 @@ int b200corr_merge_forward(const float *in1, const float *in2, float *merged, in
   B200_CHECK(in1 && in2 && merged, "merge_forward: null pointer");
   B200_CHECK(b200::sampler_fast_applicable(B, C, H, W, q, B200CORR_F32, 0),
              "merge_forward: only the register-blocked structure is fused (patch 21 / dilation_patch 2 or patch 9 / 1, "
-             "W %% 4 == 0, C %% 8 == 0); got patch %d dilation_patch %d C %d W %d", patch, dilation_patch, C, W);
+             "W %% 4 == 0); got patch %d dilation_patch %d C %d W %d", patch, dilation_patch, C, W);
   const long long HW = (long long)H * W;
   B200_CHECK((((uintptr_t)merged) & 15) == 0 && (HW * c_off) % 4 == 0 && (HW * c_total) % 4 == 0,
              "merge_forward: the slice must be 16-byte aligned");

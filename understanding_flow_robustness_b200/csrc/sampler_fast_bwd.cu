@@ -64,6 +64,7 @@ struct BwdParams {
   const int *plan;   // optional LPT schedule: [grid+1] offsets then unit ids (device memory), or nullptr
   int B, C, H, W, dpH, NCT, NCB, total_units;
   int wide_store;   // W % 8 == 0 and 32-byte aligned gradient: 256-bit stores
+  int ctail;        // C % CH_UNIT != 0: map_other is 4-D (W, H, C, B), channels past C read as zero and are not stored
   b200::SamplerGroups g;   // prefix[] unused here (every group has NCT*NCB units)
 };
 
@@ -218,8 +219,11 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
       bytes += 4 * PW * NC * 4;
     }
     mbar_arrive_expect_tx(&full_bar[st], bytes);
-    tma_load_3d(dst, &map_other, &full_bar[st], px.c0 - Cfg::HALO, R * p.dpH + px.rp,
-                px.n * p.C + px.cb * Cfg::CH_UNIT);
+    if (p.ctail)
+      tma_load_4d(dst, &map_other, &full_bar[st], px.c0 - Cfg::HALO, R * p.dpH + px.rp, px.cb * Cfg::CH_UNIT, px.n);
+    else
+      tma_load_3d(dst, &map_other, &full_bar[st], px.c0 - Cfg::HALO, R * p.dpH + px.rp,
+                  px.n * p.C + px.cb * Cfg::CH_UNIT);
     float *gd = dst + Cfg::OTHER_FLOATS;
     if (Cfg::WHICH == 1) {
       for (int l = 0; l < 4; ++l) {
@@ -288,9 +292,12 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
       const size_t HW = (size_t)p.H * p.W;
       float *o = gin + ((size_t)x.n * p.C + x.cb * Cfg::CH_UNIT + lj) * HW +
                  (size_t)h * p.W + x0;
+      const int ch0 = x.cb * Cfg::CH_UNIT + lj;   // channel of ci = 0 (ci-th channel: ch0 + 16 ci)
+      const int nci = !p.ctail ? Cfg::NCH : (p.C - ch0 + 15) / 16;   // channels of this lane that exist
       if (p.wide_store && x0 + 4 < p.W) {
 #pragma unroll
         for (int ci = 0; ci < Cfg::NCH; ++ci)   // one 32-byte sector per (channel, row): STG.256
+          if (ci < nci)
           asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + (size_t)ci * 16 * HW),
                        "f"(acc[0][ci].x), "f"(acc[0][ci].y), "f"(acc[1][ci].x), "f"(acc[1][ci].y),
                        "f"(acc[2][ci].x), "f"(acc[2][ci].y), "f"(acc[3][ci].x), "f"(acc[3][ci].y)
@@ -298,10 +305,10 @@ sampler_bwd_kernel(const __grid_constant__ CUtensorMap map_other, const __grid_c
       } else
 #pragma unroll
       for (int ci = 0; ci < Cfg::NCH; ++ci) {
-        if (x0 < p.W)
+        if (x0 < p.W && ci < nci)
           *reinterpret_cast<float4 *>(o + (size_t)ci * 16 * HW) =
               make_float4(acc[0][ci].x, acc[0][ci].y, acc[1][ci].x, acc[1][ci].y);
-        if (x0 + 4 < p.W)
+        if (x0 + 4 < p.W && ci < nci)
           *reinterpret_cast<float4 *>(o + (size_t)ci * 16 * HW + 4) =
               make_float4(acc[2][ci].x, acc[2][ci].y, acc[3][ci].x, acc[3][ci].y);
       }
@@ -317,7 +324,8 @@ int bwd_geometry(BwdParams &p, int B, int C, int H, int W, int dpH) {
   p.wide_store = 0;
   p.B = B; p.C = C; p.H = H; p.W = W; p.dpH = dpH;
   p.NCT = (W + Cfg::COLS - 1) / Cfg::COLS;
-  p.NCB = C / Cfg::CH_UNIT;
+  p.NCB = (C + Cfg::CH_UNIT - 1) / Cfg::CH_UNIT;
+  p.ctail = (C % Cfg::CH_UNIT != 0) ? 1 : 0;
   int ng = 0;
   for (int rp = 0; rp < dpH; ++rp) {
     const int NS = b200::sublattice_rows(H, dpH, rp);
@@ -395,10 +403,10 @@ int launch_bwd(const float *other, const float *gout, float *gin, int B, int C, 
 
   CUtensorMap map_o, map_g;
   {
-    const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * C};
-    const uint64_t strides[3] = {4, (uint64_t)W * 4, (uint64_t)H * W * 4};
-    const uint32_t box[3] = {(uint32_t)Cfg::NC, 1, (uint32_t)Cfg::CH_UNIT};
-    if (int e = b200::make_tensor_map(&map_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, other, dims,
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, p.ctail ? (uint64_t)C : (uint64_t)B * C, (uint64_t)B};
+    const uint64_t strides[4] = {4, (uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)H * W * 4 * C};
+    const uint32_t box[4] = {(uint32_t)Cfg::NC, 1, (uint32_t)Cfg::CH_UNIT, 1};
+    if (int e = b200::make_tensor_map(&map_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.ctail ? 4 : 3, other, dims,
                                       strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
       return e;
@@ -495,8 +503,10 @@ bool sampler_fast_applicable(int B, int C, int H, int W, const int *q, int dtype
   int ng = 0;
   for (int rp = 0; rp < dpH; ++rp) ng += (sublattice_rows(H, dpH, rp) + kRowsPerGroup - 1) / kRowsPerGroup;
   if (ng > kSamplerMaxGroups) return false;
-  if (backward) return C % 32 == 0;
-  return C % 8 == 0;
+  // any channel count: chunks that do not tile C exactly read zeros past C through 4-D tensor maps
+  // (backward: only the 32-channel units; the 128-channel units are picked for C % 128 == 0)
+  (void)backward;
+  return C >= 1;
 }
 
 }  // namespace b200

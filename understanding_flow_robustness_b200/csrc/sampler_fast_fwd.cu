@@ -84,6 +84,7 @@ struct FwdParams {
   long long out_bstride;
   float post_scale, post_slope;
   b200::SamplerGroups g;
+  int ctail;        // C % CC != 0: the maps are 4-D (W, H, C, B) so that TMA zero-fills the channels past C
 };
 
 // in2 sub-row range [Rlo, Rlo + nR) a row group needs, and its split into units of <= SLOTS items
@@ -135,7 +136,9 @@ __device__ __forceinline__ void stg256(float *p, float2 a, float2 b, float2 c, f
 
 // Fused merge block: out is the channel slice [c_off, c_off + PH*PW) of a (B, c_total, H, W) tensor (batch
 // stride p.out_bstride) and receives leaky_relu(sum * (1/C), slope) -- submodules.py:124-138 + FlowNetC.py:138,147.
-template <class Cfg>
+// CTAIL: C % CC != 0, 4-D tensor maps (a compile-time switch: the extra branch in the producer costs the
+// non-tail kernel its spill-free register allocation, 0.273 -> 0.277 ms).
+template <class Cfg, bool CTAIL>
 __global__ void __launch_bounds__(256, 1)
 sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                    float *__restrict__ out, const FwdParams p) {
@@ -168,7 +171,7 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
   __syncthreads();
 
   const int nunits = p.total_units;
-  const int cpu = p.C / CC;  // channel chunks per unit
+  const int cpu = CTAIL ? (p.C + CC - 1) / CC : p.C / CC;  // channel chunks per unit (CTAIL: the last one zero-filled past C)
 
   // ---- producer state (thread 0 only): the load stream runs NST-1 chunks ahead of the math
   int pu = blockIdx.x, pc = 0;
@@ -179,11 +182,17 @@ sampler_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
     const int st = pq % NST;
     float *dst = smem + st * Cfg::STAGE_FLOATS;
     mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
-    const int ch = px.n * p.C + pc * CC;
-    tma_load_3d(dst, &map2, &full_bar[st], px.g0 * Cfg::T - Cfg::HALO,
-                px.Rlo * p.dpH + px.rp, ch);
-    tma_load_3d(dst + Cfg::IN2_FLOATS, &map1, &full_bar[st], px.g0 * Cfg::T,
-                px.s0 * p.dpH + px.rp, ch);
+    if constexpr (CTAIL) {
+      tma_load_4d(dst, &map2, &full_bar[st], px.g0 * Cfg::T - Cfg::HALO, px.Rlo * p.dpH + px.rp, pc * CC, px.n);
+      tma_load_4d(dst + Cfg::IN2_FLOATS, &map1, &full_bar[st], px.g0 * Cfg::T, px.s0 * p.dpH + px.rp, pc * CC,
+                  px.n);
+    } else {
+      const int ch = px.n * p.C + pc * CC;
+      tma_load_3d(dst, &map2, &full_bar[st], px.g0 * Cfg::T - Cfg::HALO,
+                  px.Rlo * p.dpH + px.rp, ch);
+      tma_load_3d(dst + Cfg::IN2_FLOATS, &map1, &full_bar[st], px.g0 * Cfg::T,
+                  px.s0 * p.dpH + px.rp, ch);
+    }
     ++pq;
     if (++pc == cpu) {
       pc = 0;
@@ -355,26 +364,37 @@ int launch_fwd(const float *in1, const float *in2, float *out, int B, int C, int
   if (p.total_units == 0) return 0;
 
   CUtensorMap map1, map2;
-  const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * C};
-  const uint64_t strides[3] = {4, (uint64_t)W * 4, (uint64_t)H * W * 4};
-  const uint32_t estr[3] = {1, (uint32_t)dpH, 1};
-  const uint32_t box2[3] = {(uint32_t)Cfg::NC2, (uint32_t)((Cfg::NRB - 1) * dpH + 1), (uint32_t)Cfg::CC};
-  const uint32_t box1[3] = {(uint32_t)Cfg::NC1, (uint32_t)((b200::kRowsPerGroup - 1) * dpH + 1),
-                            (uint32_t)Cfg::CC};
-  if (int e = b200::make_tensor_map(&map2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, in2, dims, strides,
+  // (W, H, B*C) when the channel chunks tile C exactly; (W, H, C, B) otherwise (PWC-Net's 196-channel level):
+  // the last chunk of a sample then reads zeros past C instead of the next sample's channels
+  p.ctail = (C % Cfg::CC != 0) ? 1 : 0;
+  const int rank = p.ctail ? 4 : 3;
+  const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, p.ctail ? (uint64_t)C : (uint64_t)B * C, (uint64_t)B};
+  const uint64_t strides[4] = {4, (uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)H * W * 4 * C};
+  const uint32_t estr[4] = {1, (uint32_t)dpH, 1, 1};
+  const uint32_t box2[4] = {(uint32_t)Cfg::NC2, (uint32_t)((Cfg::NRB - 1) * dpH + 1), (uint32_t)Cfg::CC, 1};
+  const uint32_t box1[4] = {(uint32_t)Cfg::NC1, (uint32_t)((b200::kRowsPerGroup - 1) * dpH + 1),
+                            (uint32_t)Cfg::CC, 1};
+  if (int e = b200::make_tensor_map(&map2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, in2, dims, strides,
                                     box2, CU_TENSOR_MAP_SWIZZLE_NONE,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, estr))
     return e;
-  if (int e = b200::make_tensor_map(&map1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, in1, dims, strides,
+  if (int e = b200::make_tensor_map(&map1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, in1, dims, strides,
                                     box1, CU_TENSOR_MAP_SWIZZLE_NONE,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, estr))
     return e;
 
-  auto kern = sampler_fwd_kernel<Cfg>;
-  static bool attr_done[64] = {};  // per (kernel instantiation, device)
-  if (int e = b200::set_max_smem_once((const void *)kern, Cfg::SMEM_BYTES, attr_done)) return e;
   const int grid = p.total_units < b200::num_sms() ? p.total_units : b200::num_sms();
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(map1, map2, out, p);
+  if (p.ctail) {
+    auto kern = sampler_fwd_kernel<Cfg, true>;
+    static bool attr_done[64] = {};  // per (kernel instantiation, device)
+    if (int e = b200::set_max_smem_once((const void *)kern, Cfg::SMEM_BYTES, attr_done)) return e;
+    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(map1, map2, out, p);
+  } else {
+    auto kern = sampler_fwd_kernel<Cfg, false>;
+    static bool attr_done[64] = {};
+    if (int e = b200::set_max_smem_once((const void *)kern, Cfg::SMEM_BYTES, attr_done)) return e;
+    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(map1, map2, out, p);
+  }
   B200_LAUNCH_OK("sampler_fwd_kernel");
   return 0;
 }
