@@ -109,6 +109,25 @@ def test_merge_full_size_properties():
     assert torch.equal(fo, uo) and torch.equal(fa, a.grad) and torch.equal(fb, b.grad)
 
 
+def test_merge_pwc_call_site_layout():
+    """PWCNet.py:286-292: x = cat((leakyRELU(corr(c15, warp5)), c15, up_flow6, up_feat6), 1), C = 196 (channel tail)."""
+    from understanding_flow_robustness_b200 import correlate_merge, spatial_correlation_sample
+    torch.manual_seed(3)
+    c1 = torch.randn(2, 196, 6, 20, device="cuda", requires_grad=True)
+    w2 = torch.randn(2, 196, 6, 20, device="cuda", requires_grad=True)
+    flow = torch.randn(2, 2, 6, 20, device="cuda", requires_grad=True)
+    feat = torch.randn(2, 2, 6, 20, device="cuda", requires_grad=True)
+    g = torch.randn(2, 81 + 196 + 4, 6, 20, device="cuda")
+    x = correlate_merge(c1, w2, None, 9, 1, 0.1, after=(c1, flow, feat))
+    grads = torch.autograd.grad(x, (c1, w2, flow, feat), g)
+    corr = spatial_correlation_sample(c1, w2, kernel_size=1, patch_size=9, stride=1)
+    ref = torch.cat((F.leaky_relu(corr.view(2, 81, 6, 20) / 196, 0.1), c1, flow, feat), 1)
+    rgrads = torch.autograd.grad(ref, (c1, w2, flow, feat), g)
+    assert x.shape == ref.shape and _rel(x.detach().cpu(), ref.detach().cpu()) <= 2e-7
+    for a, b in zip(grads, rgrads):
+        assert _rel(a.cpu(), b.cpu()) <= 1e-6
+
+
 def test_merge_rejects_what_it_does_not_cover():
     from understanding_flow_robustness_b200 import correlate_merge
     a = torch.randn(1, 16, 8, 16, device="cuda")

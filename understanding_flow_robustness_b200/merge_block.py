@@ -78,34 +78,56 @@ def merge_backward(input1, input2, merged, grad_merged, c_off, patch_size=21, di
 
 
 class CorrelateMergeFunction(Function):
+    """forward(input1, input2, patch_size, dilation_patch, negative_slope, n_before, *others): the concat of
+    others[:n_before], the activated correlation and others[n_before:] along dim 1."""
+
     @staticmethod
-    def forward(ctx, input1, input2, redir, patch_size, dilation_patch, negative_slope):
-        _check("correlate_merge", input1, input2, redir)
+    def forward(ctx, input1, input2, patch_size, dilation_patch, negative_slope, n_before, *others):
+        _check("correlate_merge", input1, input2, *others)
         B, _, H, W = input1.shape
-        if redir.dim() != 4 or redir.shape[0] != B or tuple(redir.shape[2:]) != (H, W):
-            raise RuntimeError("correlate_merge: `redir` must be (B, c_redir, H, W) like the feature maps")
-        c_redir = redir.shape[1]
-        merged = torch.empty((B, c_redir + patch_size * patch_size, H, W), dtype=torch.float32, device=input1.device)
-        merged[:, :c_redir].copy_(redir)
-        merge_forward(input1, input2, merged, c_redir, patch_size, dilation_patch, negative_slope)
+        for t in others:
+            if t.dim() != 4 or t.shape[0] != B or tuple(t.shape[2:]) != (H, W):
+                raise RuntimeError("correlate_merge: concatenated tensors must be (B, c, H, W) like the feature maps")
+        widths = [t.shape[1] for t in others]
+        c_off = sum(widths[:n_before])
+        P2 = patch_size * patch_size
+        merged = torch.empty((B, sum(widths) + P2, H, W), dtype=torch.float32, device=input1.device)
+        at = 0
+        for i, t in enumerate(others):
+            if i == n_before:
+                at += P2
+            merged[:, at:at + widths[i]].copy_(t)
+            at += widths[i]
+        merge_forward(input1, input2, merged, c_off, patch_size, dilation_patch, negative_slope)
         ctx.save_for_backward(input1, input2, merged)
-        ctx.hyper = (c_redir, patch_size, dilation_patch, negative_slope)
+        ctx.hyper = (c_off, patch_size, dilation_patch, negative_slope, n_before, widths)
         return merged
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_merged):
         input1, input2, merged = ctx.saved_tensors
-        c_redir, patch_size, dilation_patch, negative_slope = ctx.hyper
+        c_off, patch_size, dilation_patch, negative_slope, n_before, widths = ctx.hyper
         g1 = g2 = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            g1, g2 = merge_backward(input1, input2, merged, grad_merged, c_redir, patch_size, dilation_patch,
+            g1, g2 = merge_backward(input1, input2, merged, grad_merged, c_off, patch_size, dilation_patch,
                                     negative_slope)
-        g_redir = grad_merged[:, :c_redir] if ctx.needs_input_grad[2] else None
-        return g1, g2, g_redir, None, None, None
+        g_others = []
+        at = 0
+        for i, w in enumerate(widths):
+            if i == n_before:
+                at += patch_size * patch_size
+            g_others.append(grad_merged[:, at:at + w] if ctx.needs_input_grad[6 + i] else None)
+            at += w
+        return (g1, g2, None, None, None, None, *g_others)
 
 
-def correlate_merge(input1, input2, redir, patch_size=21, dilation_patch=2, negative_slope=0.1):
-    """cat((redir, leaky_relu(correlate(input1, input2), negative_slope)), 1) -- FlowNetC.py:133-147."""
-    return CorrelateMergeFunction.apply(input1.contiguous(), input2.contiguous(), redir, patch_size, dilation_patch,
-                                        negative_slope)
+def correlate_merge(input1, input2, redir=None, patch_size=21, dilation_patch=2, negative_slope=0.1, after=()):
+    """cat((redir, leaky_relu(correlate(input1, input2), negative_slope), *after), 1).
+
+    FlowNetC (FlowNetC.py:133-147): `correlate_merge(conv3a, conv3b, conv_redir(conv3a))`.
+    PWC-Net (PWCNet.py:286-292, `x = cat((corr5, c15, up_flow6, up_feat6), 1)` after `leakyRELU(corr(c15, warp5))`):
+    `correlate_merge(c15, warp5, None, 9, 1, 0.1, after=(c15, up_flow6, up_feat6))`."""
+    before = () if redir is None else (redir,)
+    return CorrelateMergeFunction.apply(input1.contiguous(), input2.contiguous(), patch_size, dilation_patch,
+                                        negative_slope, len(before), *before, *after)
