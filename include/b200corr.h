@@ -136,6 +136,16 @@ int b200corr_merge_backward(const float *in1, const float *in2, const float *mer
                             size_t plan_workspace_bytes, int B, int C, int H, int W, int patch, int dilation_patch,
                             int c_total, int c_off, float slope, void *stream);
 
+/* ---------------------------------------------------------------- PWC-Net warp
+ * out[b,c,y,x] = mask * bilinear(in[b,c], position of (x + flow[b,0,y,x], y + flow[b,1,y,x]))  -- PWCDCNet.warp,
+ * models/PWCNet.py:164-204: grid_sample (bilinear, zeros padding, align_corners=False on a grid normalised with
+ * W-1 / H-1, exactly as the reference calls it) of the map and of an all-ones map, mask = [ones-sample >= 1e-4].
+ * in / out (B,C,H,W), flow (B,2,H,W), fp32.  backward zero-fills and accumulates grad_in (atomics, as
+ * grid_sample's own backward) and grad_flow; the mask passes no gradient. */
+int b200corr_warp_forward(const float *in, const float *flow, float *out, int B, int C, int H, int W, void *stream);
+int b200corr_warp_backward(const float *in, const float *flow, const float *grad_out, float *grad_in, float *grad_flow,
+                           int B, int C, int H, int W, void *stream);
+
 /* ---------------------------------------------------------------- RAFT CorrBlock */
 
 /* Level l has shape (B*H*W, 1, H_l, W_l), H_0 = H, H_{l+1} = H_l / 2 (floor), same for W. */

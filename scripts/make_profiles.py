@@ -48,7 +48,8 @@ with open(os.path.join(P, f"{R}_bench_kernel_shares.txt"), "w") as f:
 # ---- full captures
 summ = os.path.join(ROOT, "scripts", "ncu_summary.py")
 for name, what in (("sampler_full", "sampler"), ("raft_full", "raft: all-pairs + lookup forward"),
-                   ("raft_aux_full", "raft: lookup backward + alt_cuda_corr forward")):
+                   ("raft_aux_full", "raft: lookup backward + alt_cuda_corr forward"),
+                   ("merge_full", "fused FlowNetC merge block: forward kernel (1/C + LeakyReLU epilogue, concat slice) + backward pre-pass")):
     rep = os.path.join(G, f"{R}_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue

@@ -14,5 +14,7 @@ ncu --set full --clock-control none --import-source on -k "regex:allpairs_tc|loo
     python scripts/run_raft_once.py 4 2 > $O/ncu_raft.log 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:lookup_bwd|altcorr_fwd" -s 2 -c 2 -f -o $O/${R}_raft_aux_full \
     python scripts/run_raft_aux_once.py > $O/ncu_raft_aux.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:merge_grad|sampler_fwd" -s 2 -c 2 -f -o $O/${R}_merge_full \
+    python scripts/run_merge_once.py > $O/ncu_merge.log 2>&1
 python scripts/ref_cuda_compare.py > $O/ref_compare.log 2>&1; tail -3 $O/ref_compare.log
 ls -la $O | tail -12

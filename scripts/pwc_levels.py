@@ -1,6 +1,7 @@
 """the PWC-Net correlation call sites (models/PWCNet.py:42-50: patch 9, dilation_patch 1)
 at the five pyramid levels of a 384x1280 input, batch 8 -- this library vs the reference's CUDA kernels
-compiled for sm_100a (oracle/_ref).  Writes gpurun_out/r1_pwc_levels.json."""
+compiled for sm_100a (oracle/_ref); plus warp() (PWCNet.py:164-204) as one kernel vs the reference's torch ops
+(restated in oracle/warp_oracle.py) on the same GPU.  Writes gpurun_out/r1_pwc_levels.json."""
 import json
 import os
 import sys
@@ -8,8 +9,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from oracle import build_ref_cuda
-from understanding_flow_robustness_b200 import _lib, backend
+from oracle import build_ref_cuda, warp_oracle
+from understanding_flow_robustness_b200 import _lib, backend, warp
 
 q = (1, 1, 9, 9, 0, 0, 1, 1, 1, 1, 1, 1)
 B = 8
@@ -50,6 +51,21 @@ for lvl, C, H, W in LEVELS:
         row["reference_cuda_bwd_ms"] = timeit(lambda: ref.backward(a, b, g, *q), n=3, warm=1)
         o1, o2 = backend.forward(a, b, *q), ref.forward(a, b, *q)
         row["max_rel_diff_fwd"] = float((o1 - o2).abs().max() / o2.abs().max())
+    if lvl < 6:   # warp() runs in front of every correlation below the top level (PWCNet.py:293-339)
+        xw = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+        fw = (2.0 * torch.randn(B, 2, H, W, device="cuda")).requires_grad_()
+
+        def fb(fn):
+            def run():
+                o = fn(xw, fw)
+                torch.autograd.grad(o, (xw, fw), g[:, 0, 0, None].expand_as(o).contiguous())
+            return run
+        with torch.no_grad():
+            row["warp_ours_fwd_ms"] = timeit(lambda: warp(xw, fw))
+            row["warp_reference_fwd_ms"] = timeit(lambda: warp_oracle.warp(xw, fw))
+            row["warp_max_rel_diff"] = float((warp(xw, fw) - warp_oracle.warp(xw, fw)).abs().max() / warp_oracle.warp(xw, fw).abs().max())
+        row["warp_ours_fwd_bwd_ms"] = timeit(fb(warp))
+        row["warp_reference_fwd_bwd_ms"] = timeit(fb(warp_oracle.warp))
     rows.append(row)
     print(json.dumps(row))
 os.makedirs("gpurun_out", exist_ok=True)

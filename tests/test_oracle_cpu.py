@@ -118,3 +118,22 @@ def test_sampler_oracle_live_against_compiled_reference():
         o1, o2 = sampler_oracle.backward(a, b, g, k, p, s, pad, dil, dp)
         np.testing.assert_array_equal(o1, r1.numpy())
         np.testing.assert_array_equal(o2, r2.numpy())
+
+
+WARP = sorted(glob.glob(os.path.join(GOLDEN, "warp_*.npz")))
+
+
+@pytest.mark.parametrize("path", WARP, ids=[os.path.basename(p)[:-4] for p in WARP])
+def test_warp_oracle_matches_reference_golden(path):
+    """oracle/warp_oracle.py vs vectors from the reference's own PWCDCNet.warp (oracle/make_golden_warp.py)."""
+    import torch
+
+    from oracle import warp_oracle
+    z = np.load(path)
+    x = torch.from_numpy(z["x"]).requires_grad_()
+    flo = torch.from_numpy(z["flo"]).requires_grad_()
+    out = warp_oracle.warp(x, flo)
+    gx, gf = torch.autograd.grad(out, (x, flo), torch.from_numpy(z["gout"]))
+    np.testing.assert_array_equal(out.detach().numpy(), z["out"])
+    np.testing.assert_allclose(gx.numpy(), z["gx"], rtol=0, atol=1e-6 * np.abs(z["gx"]).max())
+    np.testing.assert_allclose(gf.numpy(), z["gflo"], rtol=0, atol=1e-6 * np.abs(z["gflo"]).max())

@@ -4,6 +4,8 @@ Public surface (same names / signatures as the reference's operator API):
   spatial_correlation_sample, SpatialCorrelationSampler, SpatialCorrelationSamplerFunction
       <- models/Pytorch-Correlation-extension/Correlation_Module/spatial_correlation_sampler/
   CorrBlock, AlternateCorrBlock, alt_cuda_corr            <- models/raft/corr.py, models/alt_cuda_corr/
+  warp              PWC-Net's warp() (grid_sample of the map and of a ones mask, threshold, multiply) as one kernel
+      <- models/PWCNet.py:164-204
   correlate_merge   correlate() -> LeakyReLU -> cat of the FlowNetC merge block as one kernel
       <- models/submodules.py:124-138 + models/FlowNetC.py:133-147
   install_reference_shims()  registers `spatial_correlation_sampler`, `spatial_correlation_sampler_backend`
@@ -30,6 +32,10 @@ def __getattr__(name):
         from . import merge_block
 
         return getattr(merge_block, name)
+    if name == "warp":
+        from .pwc_warp import warp
+
+        return warp
     if name == "install_reference_shims":
         from .shims import install_reference_shims
 
