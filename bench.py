@@ -632,6 +632,16 @@ def raft_bench(dev):
         gather_grows = float(gr.value)
         alt = AlternateCorrBlock(f1, f2, c["levels"], c["radius"])
         alt_ms = timed(lambda: alt(coords[0]), 3)
+        # the same block with every level on the alt_cuda_corr kernel (the reference's structure), with level 1
+        # dense as well, and what building the block costs once per RAFT forward
+        alt_rows = {}
+        for name, dmk in (("pure_alt_cuda_corr", 0), ("dense_max_keys_2048", 2048)):
+            a2 = AlternateCorrBlock(f1, f2, c["levels"], c["radius"], dense_max_keys=dmk)
+            alt_rows[name + "_ms_per_iter"] = timed(lambda: a2(coords[0]), 3)
+            del a2
+        alt_rows["block_init_ms"] = timed(lambda: AlternateCorrBlock(f1, f2, c["levels"], c["radius"]), 3)
+        alt_rows["dense_levels_from"] = alt._dense_from
+        alt_rows["dense_bytes"] = int(sum(v.numel() * 4 for v in alt._dense))
         # extra rows of the same path (not part of ms/iter): lookup backward into a resident gradient pyramid,
         # and the volume in split-TF32 (fp32-level accuracy on the tensor cores)
         from understanding_flow_robustness_b200 import raft_corr
@@ -655,7 +665,7 @@ def raft_bench(dev):
     src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     return {"metric": "RAFT corr+lookup ms/iter", "ms_per_iter": (build_ms + c["iters"] * look_ms) / c["iters"],
             "build_ms": build_ms, "lookup_ms": look_ms, "alt_corr_ms_per_iter": alt_ms,
-            "lookup_backward_ms": lookup_bwd_ms, "build_tf32x3_ms": build_x3_ms,
+            "alt_corr": alt_rows, "lookup_backward_ms": lookup_bwd_ms, "build_tf32x3_ms": build_x3_ms,
             "config": f"B={B}, {C}x{H}x{W}, {c['levels']} levels, radius {c['radius']}, {c['iters']} lookups, TF32 volume",
             "timed_loop": {"build": how_build, "lookups": how_look},
             "roofline_build": {"bound": "hbm", "achieved": vol_bytes / (build_ms * 1e-3) / 1e9, "peak": hbm,
