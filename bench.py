@@ -389,6 +389,31 @@ def main():
     e2e_value = world * B * e2e_steps / (float(t.item()) * 1e-3)
     h2d = sum(x.numel() for x in h_sets[0][:3]) * 4
     d2h = sum(x.numel() for x in h_sets[0][3:]) * 4
+    # the roof of this number: the same copies with no kernels in between (both directions at once, as the
+    # pipeline runs them), same pinned buffers, same slots
+    s_a, s_b = pipe.s_in, pipe.s_out
+    pe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    reps = 6
+    pe[0].record()
+    s_a.wait_event(pe[0])
+    s_b.wait_event(pe[0])
+    for k in range(reps):
+        hs, di, do = h_sets[k % nset], pipe.dev_in[k % pipe.depth], pipe.dev_out[k % pipe.depth]
+        with torch.cuda.stream(s_a):
+            for d, h_ in zip(di, hs[:3]):
+                d.copy_(h_, non_blocking=True)
+        with torch.cuda.stream(s_b):
+            for h_, d in zip(hs[3:], do):
+                h_.copy_(d, non_blocking=True)
+    torch.cuda.current_stream().wait_stream(s_a)
+    torch.cuda.current_stream().wait_stream(s_b)
+    pe[1].record()
+    torch.cuda.synchronize()
+    copy_ms = pe[0].elapsed_time(pe[1]) / reps
+    e2e_roof = {"copies_only_ms_per_step": copy_ms, "pairs_per_s": B / (copy_ms * 1e-3),
+                "gb_per_s_each_way": h2d / (copy_ms * 1e-3) / 1e9,
+                "what": "H2D and D2H of one step's buffers, concurrently, no kernels (this rank alone)"}
     del pipe
     os.sched_setaffinity(0, all_cpus)   # the CPU baseline below uses every host core
 
@@ -428,6 +453,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(world), timed_loop=timed_loop), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "pcie_roof": e2e_roof, "frac_of_pcie_roof": e2e_value / world / e2e_roof["pairs_per_s"],
                     "how": "pinned host in1/in2/grad_out -> device -> fwd+bwd -> pinned host out/grad_in1/grad_in2, every step; "
                            "3-stream double-buffered pipeline, wall-clock over the steps incl. final drain" + ("; host buffers on the GPU's NUMA node" if near else "")},
             "gpu_launches": int(launches), "roofline": roofline}
