@@ -651,11 +651,31 @@ def raft_bench(dev):
         import ctypes
 
         from understanding_flow_robustness_b200 import _lib
-        lvl0 = blk[0].corr_pyramid[0]
+        lvl0 = blk[0]._levels[0]   # (the probe only needs the memory region: layout-agnostic)
         gr = ctypes.c_float(0.0)
         _lib.check(_lib.lib().b200corr_measure_gather_peak(_lib.ptr(lvl0), B * H * W, H * W * 4, W * 4,
                                                            ctypes.byref(gr), _lib.current_stream(dev)), "gather peak")
         gather_grows = float(gr.value)
+        # the same two numbers with the reference's row-major volume layout (layout="rowmajor")
+        rm = [None]
+
+        def build_rm():
+            rm[0] = None
+            rm[0] = CorrBlock(f1, f2, c["levels"], c["radius"], layout="rowmajor")
+
+        def lookups_rm():
+            for cc in coords:
+                rm[0](cc)
+        blk[0] = None
+        brm_fn, _ = graphed(build_rm)
+        build_rm_ms = timed(brm_fn, 5)
+        build_rm()
+        lrm_fn, _ = graphed(lookups_rm)
+        look_rm_ms = timed(lrm_fn, 5) / c["iters"]
+        layout_mask = None
+        rm[0] = None
+        build()
+        layout_mask = blk[0]._blocked
         alt = AlternateCorrBlock(f1, f2, c["levels"], c["radius"])
         alt_ms = timed(lambda: alt(coords[0]), 3)
         # the same block with every level on the alt_cuda_corr kernel (the reference's structure), with level 1
@@ -671,7 +691,7 @@ def raft_bench(dev):
         # extra rows of the same path (not part of ms/iter): lookup backward into a resident gradient pyramid,
         # and the volume in split-TF32 (fp32-level accuracy on the tensor cores)
         from understanding_flow_robustness_b200 import raft_corr
-        glv = [torch.zeros_like(v) for v in blk[0].corr_pyramid]
+        glv = [torch.zeros_like(v) for v in blk[0]._levels]
         gout = torch.randn(B, c["levels"] * (2 * c["radius"] + 1) ** 2, H, W, device=dev)
         lbwd_fn, _ = graphed(lambda: raft_corr.lookup_backward(glv, coords[0], gout, c["radius"], H, W))
         lookup_bwd_ms = timed(lbwd_fn, 10)
@@ -690,7 +710,13 @@ def raft_bench(dev):
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     return {"metric": "RAFT corr+lookup ms/iter", "ms_per_iter": (build_ms + c["iters"] * look_ms) / c["iters"],
-            "build_ms": build_ms, "lookup_ms": look_ms, "alt_corr_ms_per_iter": alt_ms,
+            "build_ms": build_ms, "lookup_ms": look_ms,
+            "volume_layout": {"blocked_levels_mask": layout_mask,
+                              "what": "levels in the mask are stored as 8x8 tiles of 64 floats (include/b200corr.h); "
+                                      "corr_pyramid / get_corr_pyramid() convert to the reference's row-major view on demand",
+                              "rowmajor_build_ms": build_rm_ms, "rowmajor_lookup_ms": look_rm_ms,
+                              "rowmajor_ms_per_iter": (build_rm_ms + c["iters"] * look_rm_ms) / c["iters"]},
+            "alt_corr_ms_per_iter": alt_ms,
             "alt_corr": alt_rows, "lookup_backward_ms": lookup_bwd_ms, "build_tf32x3_ms": build_x3_ms,
             "config": f"B={B}, {C}x{H}x{W}, {c['levels']} levels, radius {c['radius']}, {c['iters']} lookups, TF32 volume",
             "timed_loop": {"build": how_build, "lookups": how_look},

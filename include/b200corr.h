@@ -165,6 +165,24 @@ int b200corr_allpairs_pyramid_rect(const float *f1, const float *f2, float *cons
                                    int num_levels, int B, int C, int H1, int W1, int H2, int W2, float scale,
                                    int precision, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Blocked volume layout (B200-first memory layout; no counterpart in the reference).  A blocked level stores each
+ * query's H_l x W_l slice as a row-major grid of 8x8 tiles of 64 consecutive floats:
+ *     offset(y, x) = ((y / 8) * (W_l / 8) + x / 8) * 64 + (y % 8) * 8 + x % 8
+ * so that the 10-row windows of the lookup touch 4-6 tiles of 256 B instead of 10 rows W_l * 4 bytes apart (the
+ * lookup is bound by DRAM row activations, not bytes) and the volume is written in 1 KB runs.  Bit l of
+ * `blocked_levels` = level l is blocked; b200corr_allpairs_blocked_levels() returns the mask this build supports
+ * for a problem (levels 0 and 1 when H % 16 == 0 and W % 16 == 0 and the tensor-core kernels run as CTA pairs,
+ * else 0); pass that mask or 0.  The same mask goes to b200corr_lookup_forward_layout.  The reference's
+ * observable (B*H*W, 1, H_l, W_l) row-major pyramid (corr.py:66-67) is what mask 0 produces. */
+int b200corr_allpairs_blocked_levels(int num_levels, int H, int W, int precision);
+int b200corr_allpairs_pyramid_layout(const float *f1, const float *f2, float *const *h_levels,
+                                     int num_levels, int B, int C, int H1, int W1, int H2, int W2, float scale,
+                                     int precision, int blocked_levels, void *workspace, size_t workspace_bytes,
+                                     void *stream);
+int b200corr_lookup_forward_layout(const float *const *h_levels, int num_levels, int first_level, int blocked_levels,
+                                   const float *coords, float *out, int B, int H, int W, int radius, int mode,
+                                   void *stream);
+
 /* out[B, num_levels*(2r+1)^2, H, W]; coords[B, 2, H, W] (channel 0 = x).  Channel index
  * l*(2r+1)^2 + i*(2r+1) + j, i = x-offset index, j = y-offset index (corr.py:80-86). */
 int b200corr_lookup_forward(const float *const *h_levels, int num_levels, const float *coords,

@@ -428,3 +428,49 @@ def test_full_size_raft_properties():
     ref = CorrBlock(f1[:1], f2[:1], 4, 4, precision="fp32", lookup_mode="direct")(c2[:1])
     alt = AlternateCorrBlock(f1[:1], f2[:1], 4, 4)(c2[:1])
     assert float((alt - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("shape,levels,precision,expect_mask", [
+    ((1, 32, 16, 32), 4, "tf32", 3), ((2, 64, 32, 48), 3, "tf32", 3), ((1, 16, 48, 160), 4, "tf32x3", 3),
+    ((1, 24, 16, 16), 1, "tf32", 1), ((2, 8, 16, 80), 2, "tf32", 3), ((1, 40, 64, 96), 4, "tf32", 3),
+    ((1, 32, 24, 32), 4, "tf32", 0), ((1, 32, 16, 40), 3, "tf32", 0), ((1, 32, 16, 32), 4, "fp32", 0)], ids=str)
+def test_blocked_volume_layout_equals_rowmajor(shape, levels, precision, expect_mask):
+    """The blocked layout (8x8 tiles of 64 floats, include/b200corr.h) is another element order of the same
+    values: de-blocked levels and every lookup are bit-identical to the row-major kernels."""
+    from understanding_flow_robustness_b200 import CorrBlock, coords_grid
+    B, C, H, W = shape
+    torch.manual_seed(H * W + C)
+    f1 = torch.randn(B, C, H, W, device="cuda")
+    f2 = torch.randn(B, C, H, W, device="cuda")
+    with torch.no_grad():
+        a = CorrBlock(f1, f2, levels, 4, precision=precision, layout="auto")
+        b = CorrBlock(f1, f2, levels, 4, precision=precision, layout="rowmajor")
+        assert a._blocked == expect_mask and b._blocked == 0
+        for la, lb in zip(a.get_corr_pyramid(), b.get_corr_pyramid()):
+            assert la.shape == lb.shape and torch.equal(la, lb)
+        for sigma in (0.0, 3.0, 50.0):
+            c = coords_grid(B, H, W, "cuda") + sigma * torch.randn(B, 2, H, W, device="cuda")
+            assert torch.equal(a(c), b(c))
+        for r in (1, 2, 3):
+            a.radius = b.radius = r
+            c = coords_grid(B, H, W, "cuda") + 2.0 * torch.randn(B, 2, H, W, device="cuda")
+            assert torch.equal(a(c), b(c))
+
+
+def test_blocked_layout_with_autograd():
+    """The backward never reads the forward volume: gradients are those of the row-major block."""
+    from understanding_flow_robustness_b200 import CorrBlock, coords_grid
+    torch.manual_seed(11)
+    B, C, H, W = 1, 32, 16, 32
+    f1 = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+    f2 = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+    c = coords_grid(B, H, W, "cuda") + 2.0 * torch.randn(B, 2, H, W, device="cuda")
+    g = torch.randn(B, 4 * 81, H, W, device="cuda")
+    res = []
+    for layout in ("auto", "rowmajor"):
+        blk = CorrBlock(f1, f2, 4, 4, layout=layout)
+        out = blk(c)
+        res.append((out.detach(), *torch.autograd.grad(out, (f1, f2), g)))
+        assert blk._blocked == (3 if layout == "auto" else 0)
+    for x, y in zip(*res):
+        assert torch.equal(x, y)

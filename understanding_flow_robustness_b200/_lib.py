@@ -32,6 +32,11 @@ PROTOTYPES = {
     "b200corr_allpairs_rect_workspace_bytes": (c_size_t, [c_int] * 7),
     "b200corr_allpairs_pyramid_rect": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int,
                                                c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "b200corr_allpairs_blocked_levels": (c_int, [c_int] * 4),
+    "b200corr_allpairs_pyramid_layout": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int,
+                                                 c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "b200corr_lookup_forward_layout": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                               c_int, c_int, c_int, c_int, c_void_p]),
     "b200corr_lookup_forward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_int,
                                         c_int, c_int, c_int, c_void_p]),
     "b200corr_lookup_forward_from": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p, c_int, c_int,

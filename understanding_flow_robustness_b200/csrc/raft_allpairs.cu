@@ -106,6 +106,7 @@ struct Params {
   int MT, NTY, NTX;          // tile counts (MT counts 128*CTAS-row blocks)
   float scale;
   int debug;                 // B200CORR_DEBUG bits (diagnostics): 1 skip level-0 stores, 2 skip pooled stores
+  int TW0, TW1;              // BLK kernels: 8x8 tiles per row of a level-0 / level-1 slice (W / 8, W / 16)
   float *lvl0;               // level 0
   float *lvl[3];             // levels 1..3 (nullptr if not requested)
   int LH[3], LW[3];
@@ -146,7 +147,12 @@ __device__ __forceinline__ void store_rows_coalesced(float *stage, const float (
   }
 }
 
-template <int CTAS>
+// BLK (CTA pairs only): levels 0 and 1 are written in the blocked layout -- a slice is a row-major grid of 8x8
+// tiles, each tile 64 consecutive floats (256 B).  The key patch is staged as four 8-column sub-boxes so that
+// the accumulator columns of one epilogue step (32 of them) are one half tile (4 rows x 8 columns): still one
+// 128-byte line per query row and store, but the lines of a query's patch are 1 KB contiguous, and the lookup's
+// 10-row windows touch 4-6 tiles of 256 B instead of 10 rows 640 B apart.
+template <int CTAS, bool BLK = false>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapBlo,
@@ -227,7 +233,12 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             // one arrival (the leader's) expects the bytes of both CTAs
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[st], 2 * STAGE_BYTES);
             tma_load_3d_2cta(a, ma, full_cluster[st], kb * BK, m0, b);
-            tma_load_4d_2cta(a + A_BYTES, mb, full_cluster[st], kb * BK, x0, y0 + (int)rank * (PH / 2), b);
+            if constexpr (BLK) {
+              // the key map seen as (K, x % 8, y, x / 8, b): one box lands in the order [tile column][row][column]
+              tma_load_5d_2cta(a + A_BYTES, mb, full_cluster[st], kb * BK, 0, y0 + (int)rank * (PH / 2), x0 >> 3, b);
+            } else {
+              tma_load_4d_2cta(a + A_BYTES, mb, full_cluster[st], kb * BK, x0, y0 + (int)rank * (PH / 2), b);
+            }
           } else {
             mbar_arrive_expect_tx(&full_bar[st], STAGE_BYTES);
             tma_load_3d(a, ma, &full_bar[st], kb * BK, m0, b);
@@ -303,7 +314,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       float *vol0 = p.lvl0;
       const int wrow = lane >> 3, wchunk = lane & 7;      // level 0: 4 rows x 8 chunks per instruction
       const int xrow = lane >> 2, xchunk = lane & 3;      // level 1: 8 rows x 4 chunks per instruction
-      float prev[32], p1prev[16];
+      float prev[32], p1prev[16], p2[8];
 #pragma unroll
       for (int r = 0; r < PH / 2; ++r) {
         const int pr = half * (PH / 2) + r;   // patch row
@@ -329,6 +340,19 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
         __syncwarp();
         if (!(p.debug & 1)) {
+          if constexpr (BLK) {
+            // cur = tile column r of this half: rows 4*half..4*half+3 x columns x0+8r..x0+8r+7 = half a tile
+            const size_t toff = ((size_t)(y0 >> 3) * p.TW0 + (x0 >> 3) + r) * 64 + half * 32 + 4 * wchunk;
+            const size_t slice = (size_t)p.H * p.W;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + wrow;
+              const float4 v = *reinterpret_cast<const float4 *>(ebuf + row * 128 + ((wchunk ^ (row & 7)) << 4));
+              const int mm = mrow0 + row;
+              if (mm < p.HW && x0 + 8 * r < p.W)
+                __stcs(reinterpret_cast<float4 *>(vol0 + ((size_t)bst * p.HW + mm) * slice + toff), v);
+            }
+          } else {
           const int y = y0 + pr, x = x0 + 4 * wchunk;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -338,8 +362,56 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             if (mm < p.HW && y < p.H && x < p.W)
               __stcs(reinterpret_cast<float4 *>(vol0 + (((size_t)bst * p.HW + mm) * p.H + y) * p.W + x), v);
           }
+          }
         }
-        if (r & 1) {
+        if constexpr (BLK) {
+          // 2x2 means inside the half tile: [2 rows][4 columns]
+          float p1h[8];
+#pragma unroll
+          for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+            for (int xx = 0; xx < 4; ++xx)
+              p1h[yy * 4 + xx] = (((cur[(2 * yy) * 8 + 2 * xx] + cur[(2 * yy) * 8 + 2 * xx + 1]) + cur[(2 * yy + 1) * 8 + 2 * xx]) +
+                                  cur[(2 * yy + 1) * 8 + 2 * xx + 1]) * 0.25f;
+          if (r & 1) {
+            // tile columns (r-1, r) -> level 1: [2 rows][8 columns] = 64 contiguous bytes of a level-1 tile
+            float p1[16];
+#pragma unroll
+            for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+              for (int xx = 0; xx < 4; ++xx) {
+                p1[yy * 8 + xx] = prev[yy * 4 + xx];
+                p1[yy * 8 + 4 + xx] = p1h[yy * 4 + xx];
+              }
+            if (p.lvl[0] && m_dbg) {
+              const int y1 = y0 / 2 + 2 * half;                    // first of the two level-1 rows
+              const size_t toff = ((size_t)(y1 >> 3) * p.TW1 + (x0 >> 4) + (r >> 1)) * 64 + (y1 & 7) * 8 + 4 * xchunk;
+              const size_t slice = (size_t)p.LH[0] * p.LW[0];
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4 *>(ebuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                    make_float4(p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int row = it * 8 + xrow;
+                const float4 v = *reinterpret_cast<const float4 *>(ebuf + row * 64 + ((xchunk ^ ((row >> 1) & 3)) << 4));
+                const int mm = mrow0 + row;
+                if (mm < p.HW && x0 / 2 + 8 * (r >> 1) < p.LW[0])
+                  __stcs(reinterpret_cast<float4 *>(p.lvl[0] + ((size_t)bst * p.HW + mm) * slice + toff), v);
+              }
+            }
+            // level 2 (means of the two level-1 rows): 4 of this half's 8 values per tile-column pair
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              p2[(r >> 1) * 4 + j] = (((p1[2 * j] + p1[2 * j + 1]) + p1[8 + 2 * j]) + p1[8 + 2 * j + 1]) * 0.25f;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) prev[i] = p1h[i];
+          }
+        }
+        if (BLK ? false : (r & 1)) {
           // ---- level 1: 2x2 means of rows (r-1, r) -> 16 values per query row
           float p1[16];
 #pragma unroll
@@ -370,10 +442,19 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           }
           if (r == PH / 2 - 1) {
             // ---- level 2: means of two level-1 rows -> 8 values
-            float p2[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               p2[j] = (((p1prev[2 * j] + p1prev[2 * j + 1]) + p1[2 * j]) + p1[2 * j + 1]) * 0.25f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) p1prev[j] = p1[j];
+          }
+        } else if (!BLK) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) prev[i] = cur[i];
+        }
+        {
+          if (r == PH / 2 - 1) {
             if (p.lvl[1] && m_dbg) {
               const int y2 = y0 / 4 + half, x2 = x0 / 4;
               if (y2 < p.LH[1]) {
@@ -417,13 +498,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 }
               }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) p1prev[j] = p1[j];
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) prev[i] = cur[i];
         }
       }
     }
@@ -529,7 +604,25 @@ int b200corr_allpairs_pyramid(const float *f1, const float *f2, float *const *h_
 int b200corr_allpairs_pyramid_rect(const float *f1, const float *f2, float *const *h_levels,
                                    int num_levels, int B, int C, int H1, int W1, int H, int W, float scale,
                                    int precision, void *workspace, size_t workspace_bytes, void *stream_) {
+  return b200corr_allpairs_pyramid_layout(f1, f2, h_levels, num_levels, B, C, H1, W1, H, W, scale, precision, 0,
+                                          workspace, workspace_bytes, stream_);
+}
+
+int b200corr_allpairs_blocked_levels(int num_levels, int H, int W, int precision) {
+  if (precision == B200CORR_PREC_FP32 || b200::num_sms() % 2 != 0) return 0;
+  if (H % 8 != 0 || W % 8 != 0) return 0;
+  if (num_levels == 1) return 1;
+  return (H % 16 == 0 && W % 16 == 0) ? 3 : 0;
+}
+
+int b200corr_allpairs_pyramid_layout(const float *f1, const float *f2, float *const *h_levels,
+                                     int num_levels, int B, int C, int H1, int W1, int H, int W, float scale,
+                                     int precision, int blocked_levels, void *workspace, size_t workspace_bytes,
+                                     void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK(blocked_levels == 0 || blocked_levels == b200corr_allpairs_blocked_levels(num_levels, H, W, precision),
+             "allpairs_pyramid: blocked_levels %d not available for this problem (ask b200corr_allpairs_blocked_levels)",
+             blocked_levels);
   B200_CHECK(num_levels >= 1 && num_levels <= 8, "allpairs_pyramid: num_levels must be in [1, 8]");
   B200_CHECK(B >= 0 && C >= 1 && H >= 1 && W >= 1 && H1 >= 1 && W1 >= 1, "allpairs_pyramid: bad sizes");
   B200_CHECK(precision == B200CORR_PREC_TF32 || precision == B200CORR_PREC_TF32X3 || precision == B200CORR_PREC_FP32,
@@ -558,7 +651,7 @@ int b200corr_allpairs_pyramid_rect(const float *f1, const float *f2, float *cons
     // CTA pairs (cta_group::2) by default; B200CORR_ALLPAIRS_CTAS=1 selects the single-CTA kernel
     int ctas = 2;
     {
-      const char *e = getenv("B200CORR_ALLPAIRS_CTAS");
+      const char *e = blocked_levels ? nullptr : getenv("B200CORR_ALLPAIRS_CTAS");   // the blocked layout needs CTA pairs
       if (e && atoi(e) == 1) ctas = 1;
       if (b200::num_sms() % 2) ctas = 1;
     }
@@ -589,10 +682,18 @@ int b200corr_allpairs_pyramid_rect(const float *f1, const float *f2, float *cons
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
         return e;
     }
-    {
+    if (blocked_levels) {
+      // (K, x % 8, y, x / 8, b): a [32][8][4][4] box is one half patch in tile order (see the BLK kernel)
+      const uint64_t dims[5] = {(uint64_t)Cp, 8, (uint64_t)H, (uint64_t)(W / 8), (uint64_t)B};
+      const uint64_t str[5] = {4, (uint64_t)Cp * 4, (uint64_t)W * Cp * 4, (uint64_t)8 * Cp * 4, (uint64_t)HW * Cp * 4};
+      const uint32_t box[5] = {tc::BK, 8, (uint32_t)(tc::PH / ctas), 4, 1};
+      if (int e = b200::make_tensor_map(&mapB_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, f2t_, dims, str, box,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+        return e;
+    } else {
       const uint64_t dims[4] = {(uint64_t)Cp, (uint64_t)W, (uint64_t)H, (uint64_t)B};
       const uint64_t str[4] = {4, (uint64_t)Cp * 4, (uint64_t)W * Cp * 4, (uint64_t)HW * Cp * 4};
-      const uint32_t box[4] = {tc::BK, tc::PW, (uint32_t)(tc::PH / ctas), 1};
+      const uint32_t box[4] = {tc::BK, (uint32_t)tc::PW, (uint32_t)(tc::PH / ctas), 1};
       if (int e = b200::make_tensor_map(&mapB_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, f2t_, dims, str, box,
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
         return e;
@@ -606,6 +707,7 @@ int b200corr_allpairs_pyramid_rect(const float *f1, const float *f2, float *cons
     p.NTY = (H + tc::PH - 1) / tc::PH;
     p.NTX = (W + tc::PW - 1) / tc::PW;
     p.scale = scale;
+    p.TW0 = W / 8; p.TW1 = W / 16;
     p.lvl0 = h_levels[0];
     {
       const char *dbg = getenv("B200CORR_DEBUG");
@@ -622,7 +724,7 @@ int b200corr_allpairs_pyramid_rect(const float *f1, const float *f2, float *cons
     const int total = B * p.MT * p.NTY * p.NTX;
     if (ctas == 2) {
       static bool attr_done[64] = {};  // per device
-      if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel<2>, tc::Cfg<2>::SMEM_BYTES, attr_done)) return e;
+      if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel<2, false>, tc::Cfg<2>::SMEM_BYTES, attr_done)) return e;
       const int pairs = b200::num_sms() / 2;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(2 * (total < pairs ? total : pairs));
@@ -634,12 +736,18 @@ int b200corr_allpairs_pyramid_rect(const float *f1, const float *f2, float *cons
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      B200_CUDA(cudaLaunchKernelEx(&cfg, allpairs_tc_kernel<2>, mapA, mapB, mapAlo, mapBlo, p));
+      if (blocked_levels) {
+        static bool attr_blk[64] = {};
+        if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel<2, true>, tc::Cfg<2>::SMEM_BYTES, attr_blk)) return e;
+        B200_CUDA(cudaLaunchKernelEx(&cfg, allpairs_tc_kernel<2, true>, mapA, mapB, mapAlo, mapBlo, p));
+      } else {
+        B200_CUDA(cudaLaunchKernelEx(&cfg, allpairs_tc_kernel<2, false>, mapA, mapB, mapAlo, mapBlo, p));
+      }
     } else {
       static bool attr_done[64] = {};  // per device
-      if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel<1>, tc::Cfg<1>::SMEM_BYTES, attr_done)) return e;
+      if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel<1, false>, tc::Cfg<1>::SMEM_BYTES, attr_done)) return e;
       const int grid = total < b200::num_sms() ? total : b200::num_sms();
-      allpairs_tc_kernel<1><<<grid, tc::THREADS, tc::Cfg<1>::SMEM_BYTES, stream>>>(mapA, mapB, mapAlo, mapBlo, p);
+      allpairs_tc_kernel<1, false><<<grid, tc::THREADS, tc::Cfg<1>::SMEM_BYTES, stream>>>(mapA, mapB, mapAlo, mapBlo, p);
     }
     B200_LAUNCH_OK("allpairs_tc_kernel");
   }

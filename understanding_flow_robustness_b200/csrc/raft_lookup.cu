@@ -45,6 +45,7 @@ struct LookupParams {
   int LH[kMaxLevels], LW[kMaxLevels];
   int path[kMaxLevels];  // access flavour per level (sector / 16-byte / scalar), from width and alignment
   int num_levels, B, HW, radius, mode;
+  int blocked[kMaxLevels];   // forward only: the level is stored as 8x8 tiles of 64 floats (b200corr.h)
   int first_level;   // pyramid level of list entry 0: entry i has extent (H, W) >> (first_level + i), coordinate scale 2^-(first_level + i)
 };
 
@@ -142,6 +143,7 @@ struct StageArgs {
   int ylo, yhi;        // window rows the taps touch
   int clo, chi;        // staged columns the taps touch
   bool q_ok;
+  bool blocked;        // PATH_SECTOR only: the slice is a grid of 8x8 tiles (64 consecutive floats each)
 };
 
 // Stage window rows r0 .. r0+NR-1 (those below WS) of this lane's query: win[row][column][lane].
@@ -169,8 +171,11 @@ __device__ __forceinline__ void stage_rows(float *win, int lane, const StageArgs
 #pragma unroll
       for (int g = 0; g < 3; ++g) {   // one 32-byte sector per load
         const int x = c0 + 8 * g;
-        if (row_ok && x >= 0 && x < a.LW && lhi >= 8 * g && llo < 8 * g + 8)
-          ldg256(src + 8 * g, *reinterpret_cast<float(*)[8]>(&v[r][8 * g]));
+        if (row_ok && x >= 0 && x < a.LW && lhi >= 8 * g && llo < 8 * g + 8) {
+          const float *sp = a.blocked ? a.slice + ((size_t)((y >> 3) * (a.LW >> 3) + (x >> 3)) * 64 + (y & 7) * 8)
+                                      : src + 8 * g;
+          ldg256(sp, *reinterpret_cast<float(*)[8]>(&v[r][8 * g]));
+        }
       }
     } else if (PATH == PATH_VEC4) {
 #pragma unroll
@@ -228,6 +233,7 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
   const int shift = path == PATH_SCALAR ? 0 : (a.ox & 3);
   a.clo = shift + xlo; a.chi = shift + xhi;
   a.slice = p.lvl[lvl] + ((size_t)b * p.HW + (a.q_ok ? q : 0)) * a.LH * a.LW;
+  a.blocked = p.blocked[lvl] != 0;
 
   // ---- stage this warp's rows (all of its loads are in flight together)
   if (path == PATH_SECTOR) stage_rows<PATH_SECTOR, RPW, WS>(win, lane, a, warp * RPW);
@@ -520,7 +526,7 @@ int fill_params(LookupParams &p, const float *const *lv, float *const *glv, int 
   p.num_levels = num_levels; p.B = B; p.HW = H * W; p.radius = radius; p.mode = mode; p.first_level = first_level;
   int h = H >> first_level, w = W >> first_level;
   for (int l = 0; l < kMaxLevels; ++l) {
-    p.lvl[l] = nullptr; p.glvl[l] = nullptr; p.LH[l] = 0; p.LW[l] = 0; p.path[l] = 0;
+    p.lvl[l] = nullptr; p.glvl[l] = nullptr; p.LH[l] = 0; p.LW[l] = 0; p.path[l] = 0; p.blocked[l] = 0;
     if (l < num_levels) {
       p.LH[l] = h; p.LW[l] = w;
       B200_CHECK(h >= 1 && w >= 1, "%s: pyramid level %d is empty (%dx%d input)", who, l, H, W);
@@ -544,6 +550,12 @@ int b200corr_lookup_forward(const float *const *h_levels, int num_levels, const 
 int b200corr_lookup_forward_from(const float *const *h_levels, int num_levels, int first_level,
                                  const float *coords, float *out, int B, int H, int W, int radius, int mode,
                                  void *stream_) {
+  return b200corr_lookup_forward_layout(h_levels, num_levels, first_level, 0, coords, out, B, H, W, radius, mode, stream_);
+}
+
+int b200corr_lookup_forward_layout(const float *const *h_levels, int num_levels, int first_level, int blocked_levels,
+                                   const float *coords, float *out, int B, int H, int W, int radius, int mode,
+                                   void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LookupParams p;
   if (B == 0) return 0;   // empty tensors have no storage: nothing to validate, nothing to do
@@ -552,7 +564,13 @@ int b200corr_lookup_forward_from(const float *const *h_levels, int num_levels, i
   for (int l = 0; l < num_levels; ++l) {
     const uintptr_t a = (uintptr_t)p.lvl[l];
     p.path[l] = (p.LW[l] % 8 == 0 && a % 32 == 0) ? PATH_SECTOR : (p.LW[l] % 4 == 0 && a % 16 == 0) ? PATH_VEC4 : PATH_SCALAR;
+    if ((blocked_levels >> l) & 1) {
+      B200_CHECK(p.path[l] == PATH_SECTOR && p.LH[l] % 8 == 0,
+                 "lookup_forward: level %d (%dx%d) cannot be in the blocked layout", l, p.LH[l], p.LW[l]);
+      p.blocked[l] = 1;
+    }
   }
+  B200_CHECK((blocked_levels >> num_levels) == 0, "lookup_forward: blocked_levels names a level that is not there");
   dim3 grid(((p.HW + QT - 1) / QT) * num_levels, 1, B);
   switch (radius) {
     case 1: lookup_fwd_kernel<1><<<grid, 128, 0, stream>>>(p, coords, out); break;

@@ -158,6 +158,15 @@ __device__ __forceinline__ void tma_load_4d_2cta(void *dst, const CUtensorMap *m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d_2cta(void *dst, const CUtensorMap *m, uint32_t bar_cluster,
+                                                 int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 // ---- TMEM -> registers: this warp's 32 lanes x 32 consecutive columns
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&r)[32]) {
   uint32_t u[32];

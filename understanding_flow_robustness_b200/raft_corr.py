@@ -74,8 +74,13 @@ def _level_shapes(H, W, num_levels):
 
 # ------------------------------------------------------------------------------------------------
 # raw C-ABI calls
-def allpairs_pyramid(fmap1, fmap2, num_levels=4, precision="tf32"):
-    """List of (B*H*W, 1, H_l, W_l) tensors: vol_0 = f1^T f2 / sqrt(C), vol_{l+1} = avg_pool2d(vol_l, 2, 2)."""
+def allpairs_pyramid(fmap1, fmap2, num_levels=4, precision="tf32", blocked=False):
+    """List of (B*H*W, 1, H_l, W_l) tensors: vol_0 = f1^T f2 / sqrt(C), vol_{l+1} = avg_pool2d(vol_l, 2, 2).
+
+    blocked=True returns `(levels, mask)`: the levels whose bit is set in `mask` hold each slice as a grid of 8x8
+    tiles of 64 consecutive floats (include/b200corr.h, "blocked volume layout") -- same tensor shapes, same
+    values, another element order; `deblock()` gives the reference's row-major view of such a level.  mask is 0
+    where the library has no blocked kernel for the problem."""
     fmap1 = fmap1.contiguous()
     fmap2 = fmap2.contiguous()
     _require_cuda_f32("allpairs_pyramid", fmap1, fmap2)
@@ -89,26 +94,33 @@ def allpairs_pyramid(fmap1, fmap2, num_levels=4, precision="tf32"):
     nbytes = L.b200corr_allpairs_workspace_bytes(B, C, H, W, prec)
     ws = torch.empty((max(nbytes, 1) + 127) // 128 * 32, dtype=torch.float32, device=fmap1.device)
     with torch.cuda.device(fmap1.device):
-        code = L.b200corr_allpairs_pyramid(_lib.ptr(fmap1), _lib.ptr(fmap2), _lib.ptr_array(levels), num_levels,
-                                           B, C, H, W, 1.0 / math.sqrt(C), prec, _lib.ptr(ws), nbytes,
-                                           _lib.current_stream(fmap1.device))
-    _lib.check(code, "b200corr_allpairs_pyramid")
-    return levels
+        mask = L.b200corr_allpairs_blocked_levels(num_levels, H, W, prec) if blocked and B > 0 else 0
+        code = L.b200corr_allpairs_pyramid_layout(_lib.ptr(fmap1), _lib.ptr(fmap2), _lib.ptr_array(levels), num_levels,
+                                                  B, C, H, W, H, W, 1.0 / math.sqrt(C), prec, mask, _lib.ptr(ws), nbytes,
+                                                  _lib.current_stream(fmap1.device))
+    _lib.check(code, "b200corr_allpairs_pyramid_layout")
+    return (levels, mask) if blocked else levels
 
 
-def lookup_forward(levels, coords, radius, H, W, mode="grid_sample", first_level=0):
+def deblock(level):
+    """Row-major (Q, 1, H_l, W_l) copy of a level stored in the blocked layout."""
+    Q, _, h, w = level.shape
+    return level.view(Q, h // 8, w // 8, 8, 8).permute(0, 1, 3, 2, 4).reshape(Q, 1, h, w)
+
+
+def lookup_forward(levels, coords, radius, H, W, mode="grid_sample", first_level=0, blocked_levels=0):
     """`levels[i]` is pyramid level first_level + i: extent (H, W) >> (first_level + i), sampled at
-    coords / 2^(first_level + i)."""
+    coords / 2^(first_level + i).  Bit i of `blocked_levels`: levels[i] is in the blocked layout."""
     coords = coords.contiguous()
     _require_cuda_f32("lookup_forward", coords, *levels)
     B = coords.shape[0]
     n = (2 * radius + 1) ** 2
     out = torch.empty((B, len(levels) * n, H, W), dtype=torch.float32, device=coords.device)
     with torch.cuda.device(coords.device):
-        code = _lib.lib().b200corr_lookup_forward_from(_lib.ptr_array(levels), len(levels), first_level,
-                                                       _lib.ptr(coords), _lib.ptr(out), B, H, W, radius,
-                                                       LOOKUP_MODES[mode], _lib.current_stream(coords.device))
-    _lib.check(code, "b200corr_lookup_forward_from")
+        code = _lib.lib().b200corr_lookup_forward_layout(_lib.ptr_array(levels), len(levels), first_level,
+                                                         blocked_levels, _lib.ptr(coords), _lib.ptr(out), B, H, W,
+                                                         radius, LOOKUP_MODES[mode], _lib.current_stream(coords.device))
+    _lib.check(code, "b200corr_lookup_forward_layout")
     return out
 
 
@@ -232,7 +244,7 @@ class _VolumeFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, fmap1, fmap2, block):
-        block.corr_pyramid = allpairs_pyramid(fmap1, fmap2, block.num_levels, block.precision)
+        block._build(fmap1, fmap2)
         ctx.save_for_backward(fmap1, fmap2)
         ctx.block = block
         return fmap1.new_zeros(1)
@@ -267,7 +279,8 @@ class _LookupFunction(torch.autograd.Function):
     def forward(ctx, handle, coords, block):
         ctx.block = block
         ctx.save_for_backward(coords)
-        return lookup_forward(block.corr_pyramid, coords, block.radius, block.H, block.W, block.lookup_mode)
+        return lookup_forward(block._levels, coords, block.radius, block.H, block.W, block.lookup_mode,
+                              blocked_levels=block._blocked)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -275,7 +288,9 @@ class _LookupFunction(torch.autograd.Function):
         (coords,) = ctx.saved_tensors
         block = ctx.block
         if block._grad_levels is None:
-            block._grad_levels = [torch.zeros_like(v) for v in block.corr_pyramid]
+            # the gradient pyramid is row-major whatever the layout of the forward volume (nothing in the
+            # backward reads the forward volume)
+            block._grad_levels = [torch.zeros_like(v) for v in block._levels]
         lookup_backward(block._grad_levels, coords, grad_out, block.radius, block.H, block.W, block.lookup_mode)
         return grad_out.new_zeros(1), None, None
 
@@ -284,13 +299,19 @@ class CorrBlock:
     """models/raft/corr.py:26-106."""
 
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, compute_spatial=False, precision="tf32",
-                 lookup_mode="grid_sample"):
+                 lookup_mode="grid_sample", layout="auto"):
+        """layout: "auto" keeps the two fine levels in the blocked layout (8x8 tiles, include/b200corr.h) where the
+        library supports the problem -- the lookups read them 1.4x faster; `corr_pyramid` / `get_corr_pyramid()`
+        still hand out the reference's row-major tensors (converted on first use).  "rowmajor": as the reference."""
         self.num_levels = num_levels
         self.radius = radius
         self.compute_spatial = compute_spatial
         self.precision = precision
         self.lookup_mode = lookup_mode
-        self.corr_pyramid = []
+        if layout not in ("auto", "rowmajor"):
+            raise ValueError("CorrBlock: layout must be 'auto' or 'rowmajor'")
+        self._want_blocked = layout == "auto"
+        self._levels, self._blocked, self._rowmajor = [], 0, None
         self._grad_levels = None
         self._handle = None
         if self.compute_spatial:
@@ -301,17 +322,33 @@ class CorrBlock:
             batch, ph, pw, h, w = out_corr.size()
             self.spatial_corr = out_corr.view(batch, ph * pw, h, w) / fmap1.size(1)
             corr = out_corr.view(batch * ph * pw, 1, h, w)
-            self.corr_pyramid.append(corr)
+            self._levels.append(corr)
             for _ in range(self.num_levels - 1):
                 corr = F.avg_pool2d(corr, 2, stride=2)
-                self.corr_pyramid.append(corr)
+                self._levels.append(corr)
         else:
             self.B, self.C, self.H, self.W = fmap1.shape
             needs_grad = torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad)
             if needs_grad:
                 self._handle = _VolumeFunction.apply(fmap1.contiguous(), fmap2.contiguous(), self)
             else:
-                self.corr_pyramid = allpairs_pyramid(fmap1.detach(), fmap2.detach(), num_levels, precision)
+                self._build(fmap1.detach(), fmap2.detach())
+
+    def _build(self, fmap1, fmap2):
+        if self._want_blocked:
+            self._levels, self._blocked = allpairs_pyramid(fmap1, fmap2, self.num_levels, self.precision, blocked=True)
+        else:
+            self._levels, self._blocked = allpairs_pyramid(fmap1, fmap2, self.num_levels, self.precision), 0
+        self._rowmajor = None
+
+    @property
+    def corr_pyramid(self):
+        """The pyramid in the reference's layout, corr.py:66-67: (B*H*W, 1, H_l, W_l) row-major tensors."""
+        if self._blocked == 0:
+            return self._levels
+        if self._rowmajor is None:
+            self._rowmajor = [deblock(v) if (self._blocked >> i) & 1 else v for i, v in enumerate(self._levels)]
+        return self._rowmajor
 
     def get_corr_pyramid(self):
         return self.corr_pyramid
@@ -333,7 +370,8 @@ class CorrBlock:
         coords = coords.detach().float()
         if self._handle is not None and torch.is_grad_enabled():
             return _LookupFunction.apply(self._handle, coords, self)
-        return lookup_forward(self.corr_pyramid, coords, self.radius, self.H, self.W, self.lookup_mode)
+        return lookup_forward(self._levels, coords, self.radius, self.H, self.W, self.lookup_mode,
+                              blocked_levels=self._blocked)
 
     @staticmethod
     def corr(fmap1, fmap2, precision="tf32"):
