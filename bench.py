@@ -691,7 +691,7 @@ def raft_bench(dev):
         # extra rows of the same path (not part of ms/iter): lookup backward into a resident gradient pyramid,
         # and the volume in split-TF32 (fp32-level accuracy on the tensor cores)
         from understanding_flow_robustness_b200 import raft_corr
-        glv = [torch.zeros_like(v) for v in blk[0]._levels]
+        glv = [v.new_zeros((v.shape[0], 1, H >> i, W >> i)) for i, v in enumerate(blk[0]._levels)]   # row-major gradient pyramid
         gout = torch.randn(B, c["levels"] * (2 * c["radius"] + 1) ** 2, H, W, device=dev)
         lbwd_fn, _ = graphed(lambda: raft_corr.lookup_backward(glv, coords[0], gout, c["radius"], H, W))
         lookup_bwd_ms = timed(lbwd_fn, 10)

@@ -166,14 +166,18 @@ int b200corr_allpairs_pyramid_rect(const float *f1, const float *f2, float *cons
                                    int precision, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Blocked volume layout (B200-first memory layout; no counterpart in the reference).  A blocked level stores each
- * query's H_l x W_l slice as a row-major grid of 8x8 tiles of 64 consecutive floats:
- *     offset(y, x) = ((y / 8) * (W_l / 8) + x / 8) * 64 + (y % 8) * 8 + x % 8
- * so that the 10-row windows of the lookup touch 4-6 tiles of 256 B instead of 10 rows W_l * 4 bytes apart (the
- * lookup is bound by DRAM row activations, not bytes) and the volume is written in 1 KB runs.  Bit l of
- * `blocked_levels` = level l is blocked; b200corr_allpairs_blocked_levels() returns the mask this build supports
- * for a problem (levels 0 and 1 when H % 16 == 0 and W % 16 == 0 and the tensor-core kernels run as CTA pairs,
- * else 0); pass that mask or 0.  The same mask goes to b200corr_lookup_forward_layout.  The reference's
- * observable (B*H*W, 1, H_l, W_l) row-major pyramid (corr.py:66-67) is what mask 0 produces. */
+ * query's slice as a row-major grid of 8x8 tiles of 64 consecutive floats, padded to whole tiles:
+ *     offset(y, x) = ((y / 8) * (Wp / 8) + x / 8) * 64 + (y % 8) * 8 + x % 8,   slice = Hp * Wp floats
+ * with (Hp, Wp) from b200corr_blocked_level_dims (level 0: H rounded up to 8, W; level 1: rounded up to whole tiles).
+ * Padding inside written tiles holds zeros (= the zero padding of grid_sample); rows past the level's extent are
+ * never read.  The 10-row windows of the lookup then touch 4-6 tiles of 256 B instead of 10 rows W_l * 4 bytes apart,
+ * and the volume is written in aligned 1 KB runs whatever W is (row-major rows of 480 B, e.g. 68x120 maps, make every
+ * other 128-byte store straddle two lines shared with another CTA).  Bit l of `blocked_levels` = level l is blocked;
+ * b200corr_allpairs_blocked_levels() returns the mask this build supports for a problem (levels 0 and 1 when
+ * W % 8 == 0 and the tensor-core kernels run as CTA pairs, else 0); pass that mask or 0.  The same mask goes to
+ * b200corr_lookup_forward_layout.  The reference's observable (B*H*W, 1, H_l, W_l) row-major pyramid (corr.py:66-67)
+ * is what mask 0 produces. */
+void b200corr_blocked_level_dims(int level, int H, int W, int *Hp, int *Wp);
 int b200corr_allpairs_blocked_levels(int num_levels, int H, int W, int precision);
 int b200corr_allpairs_pyramid_layout(const float *f1, const float *f2, float *const *h_levels,
                                      int num_levels, int B, int C, int H1, int W1, int H2, int W2, float scale,

@@ -33,6 +33,7 @@ PROTOTYPES = {
     "b200corr_allpairs_pyramid_rect": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int,
                                                c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "b200corr_allpairs_blocked_levels": (c_int, [c_int] * 4),
+    "b200corr_blocked_level_dims": (None, [c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "b200corr_allpairs_pyramid_layout": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int,
                                                  c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200corr_lookup_forward_layout": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p, c_int,

@@ -106,7 +106,8 @@ struct Params {
   int MT, NTY, NTX;          // tile counts (MT counts 128*CTAS-row blocks)
   float scale;
   int debug;                 // B200CORR_DEBUG bits (diagnostics): 1 skip level-0 stores, 2 skip pooled stores
-  int TW0, TW1;              // BLK kernels: 8x8 tiles per row of a level-0 / level-1 slice (W / 8, W / 16)
+  int TW0, TW1;              // BLK kernels: 8x8 tiles per row of a (padded) level-0 / level-1 slice
+  long long S0, S1;          // BLK kernels: floats per (padded) level-0 / level-1 slice
   float *lvl0;               // level 0
   float *lvl[3];             // levels 1..3 (nullptr if not requested)
   int LH[3], LW[3];
@@ -343,7 +344,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           if constexpr (BLK) {
             // cur = tile column r of this half: rows 4*half..4*half+3 x columns x0+8r..x0+8r+7 = half a tile
             const size_t toff = ((size_t)(y0 >> 3) * p.TW0 + (x0 >> 3) + r) * 64 + half * 32 + 4 * wchunk;
-            const size_t slice = (size_t)p.H * p.W;
+            const size_t slice = (size_t)p.S0;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int row = it * 4 + wrow;
@@ -386,7 +387,7 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             if (p.lvl[0] && m_dbg) {
               const int y1 = y0 / 2 + 2 * half;                    // first of the two level-1 rows
               const size_t toff = ((size_t)(y1 >> 3) * p.TW1 + (x0 >> 4) + (r >> 1)) * 64 + (y1 & 7) * 8 + 4 * xchunk;
-              const size_t slice = (size_t)p.LH[0] * p.LW[0];
+              const size_t slice = (size_t)p.S1;
               __syncwarp();
 #pragma unroll
               for (int j = 0; j < 4; ++j)
@@ -608,11 +609,17 @@ int b200corr_allpairs_pyramid_rect(const float *f1, const float *f2, float *cons
                                           workspace, workspace_bytes, stream_);
 }
 
+void b200corr_blocked_level_dims(int level, int H, int W, int *Hp, int *Wp) {
+  const int H0 = (H + 7) / 8 * 8;                 // level 0: whole tile rows; W % 8 == 0 is a precondition
+  if (level == 0) { *Hp = H0; *Wp = W; return; }
+  *Hp = (H0 / 2 + 7) / 8 * 8;                     // level 1: the H0 / 2 rows the patches produce, in whole tiles
+  *Wp = (W + 15) / 16 * 8;                        //          columns of the last tile past W / 2 hold zeros
+}
+
 int b200corr_allpairs_blocked_levels(int num_levels, int H, int W, int precision) {
   if (precision == B200CORR_PREC_FP32 || b200::num_sms() % 2 != 0) return 0;
-  if (H % 8 != 0 || W % 8 != 0) return 0;
-  if (num_levels == 1) return 1;
-  return (H % 16 == 0 && W % 16 == 0) ? 3 : 0;
+  if (W % 8 != 0 || H < 1) return 0;
+  return num_levels == 1 ? 1 : 3;
 }
 
 int b200corr_allpairs_pyramid_layout(const float *f1, const float *f2, float *const *h_levels,
@@ -707,7 +714,13 @@ int b200corr_allpairs_pyramid_layout(const float *f1, const float *f2, float *co
     p.NTY = (H + tc::PH - 1) / tc::PH;
     p.NTX = (W + tc::PW - 1) / tc::PW;
     p.scale = scale;
-    p.TW0 = W / 8; p.TW1 = W / 16;
+    {
+      int hp, wp;
+      b200corr_blocked_level_dims(0, H, W, &hp, &wp);
+      p.TW0 = wp / 8; p.S0 = (long long)hp * wp;
+      b200corr_blocked_level_dims(1, H, W, &hp, &wp);
+      p.TW1 = wp / 8; p.S1 = (long long)hp * wp;
+    }
     p.lvl0 = h_levels[0];
     {
       const char *dbg = getenv("B200CORR_DEBUG");

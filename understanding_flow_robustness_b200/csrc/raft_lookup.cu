@@ -46,6 +46,8 @@ struct LookupParams {
   int path[kMaxLevels];  // access flavour per level (sector / 16-byte / scalar), from width and alignment
   int num_levels, B, HW, radius, mode;
   int blocked[kMaxLevels];   // forward only: the level is stored as 8x8 tiles of 64 floats (b200corr.h)
+  int tiles_w[kMaxLevels];   // blocked levels: tiles per row of the padded slice
+  long long slice[kMaxLevels];   // floats per query slice (LH * LW, or the padded size of a blocked level)
   int first_level;   // pyramid level of list entry 0: entry i has extent (H, W) >> (first_level + i), coordinate scale 2^-(first_level + i)
 };
 
@@ -144,6 +146,7 @@ struct StageArgs {
   int clo, chi;        // staged columns the taps touch
   bool q_ok;
   bool blocked;        // PATH_SECTOR only: the slice is a grid of 8x8 tiles (64 consecutive floats each)
+  int tiles_w;         // tiles per row of a blocked slice
 };
 
 // Stage window rows r0 .. r0+NR-1 (those below WS) of this lane's query: win[row][column][lane].
@@ -172,7 +175,7 @@ __device__ __forceinline__ void stage_rows(float *win, int lane, const StageArgs
       for (int g = 0; g < 3; ++g) {   // one 32-byte sector per load
         const int x = c0 + 8 * g;
         if (row_ok && x >= 0 && x < a.LW && lhi >= 8 * g && llo < 8 * g + 8) {
-          const float *sp = a.blocked ? a.slice + ((size_t)((y >> 3) * (a.LW >> 3) + (x >> 3)) * 64 + (y & 7) * 8)
+          const float *sp = a.blocked ? a.slice + ((size_t)((y >> 3) * a.tiles_w + (x >> 3)) * 64 + (y & 7) * 8)
                                       : src + 8 * g;
           ldg256(sp, *reinterpret_cast<float(*)[8]>(&v[r][8 * g]));
         }
@@ -232,8 +235,9 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
   // staged column of window column 0, and the staged columns the taps touch
   const int shift = path == PATH_SCALAR ? 0 : (a.ox & 3);
   a.clo = shift + xlo; a.chi = shift + xhi;
-  a.slice = p.lvl[lvl] + ((size_t)b * p.HW + (a.q_ok ? q : 0)) * a.LH * a.LW;
+  a.slice = p.lvl[lvl] + ((size_t)b * p.HW + (a.q_ok ? q : 0)) * (size_t)p.slice[lvl];
   a.blocked = p.blocked[lvl] != 0;
+  a.tiles_w = p.tiles_w[lvl];
 
   // ---- stage this warp's rows (all of its loads are in flight together)
   if (path == PATH_SECTOR) stage_rows<PATH_SECTOR, RPW, WS>(win, lane, a, warp * RPW);
@@ -526,9 +530,9 @@ int fill_params(LookupParams &p, const float *const *lv, float *const *glv, int 
   p.num_levels = num_levels; p.B = B; p.HW = H * W; p.radius = radius; p.mode = mode; p.first_level = first_level;
   int h = H >> first_level, w = W >> first_level;
   for (int l = 0; l < kMaxLevels; ++l) {
-    p.lvl[l] = nullptr; p.glvl[l] = nullptr; p.LH[l] = 0; p.LW[l] = 0; p.path[l] = 0; p.blocked[l] = 0;
+    p.lvl[l] = nullptr; p.glvl[l] = nullptr; p.LH[l] = 0; p.LW[l] = 0; p.path[l] = 0; p.blocked[l] = 0; p.tiles_w[l] = 0; p.slice[l] = 0;
     if (l < num_levels) {
-      p.LH[l] = h; p.LW[l] = w;
+      p.LH[l] = h; p.LW[l] = w; p.slice[l] = (long long)h * w;
       B200_CHECK(h >= 1 && w >= 1, "%s: pyramid level %d is empty (%dx%d input)", who, l, H, W);
       if (lv) { B200_CHECK(lv[l], "%s: null level %d", who, l); p.lvl[l] = lv[l]; }
       if (glv) { B200_CHECK(glv[l], "%s: null gradient level %d", who, l); p.glvl[l] = glv[l]; }
@@ -565,9 +569,13 @@ int b200corr_lookup_forward_layout(const float *const *h_levels, int num_levels,
     const uintptr_t a = (uintptr_t)p.lvl[l];
     p.path[l] = (p.LW[l] % 8 == 0 && a % 32 == 0) ? PATH_SECTOR : (p.LW[l] % 4 == 0 && a % 16 == 0) ? PATH_VEC4 : PATH_SCALAR;
     if ((blocked_levels >> l) & 1) {
-      B200_CHECK(p.path[l] == PATH_SECTOR && p.LH[l] % 8 == 0,
+      // blocked levels are the two fine levels of a pyramid built by b200corr_allpairs_pyramid_layout: padded tiles,
+      // zeros in the padding columns, sector loads whatever the true width is
+      B200_CHECK(first_level == 0 && l <= 1 && W % 8 == 0 && a % 32 == 0,
                  "lookup_forward: level %d (%dx%d) cannot be in the blocked layout", l, p.LH[l], p.LW[l]);
-      p.blocked[l] = 1;
+      int hp, wp;
+      b200corr_blocked_level_dims(l, H, W, &hp, &wp);
+      p.blocked[l] = 1; p.path[l] = PATH_SECTOR; p.tiles_w[l] = wp / 8; p.slice[l] = (long long)hp * wp;
     }
   }
   B200_CHECK((blocked_levels >> num_levels) == 0, "lookup_forward: blocked_levels names a level that is not there");

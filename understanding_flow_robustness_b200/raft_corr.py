@@ -21,6 +21,7 @@ Differences from the reference, all deliberate:
   * lookups accumulate their gradient in place into ONE dense gradient pyramid per block instead of
     allocating a dense volume gradient per grid_sample call.
 """
+import ctypes
 import math
 import types
 
@@ -89,12 +90,16 @@ def allpairs_pyramid(fmap1, fmap2, num_levels=4, precision="tf32", blocked=False
     B, C, H, W = fmap1.shape
     prec = PRECISIONS[precision]
     L = _lib.lib()
-    levels = [torch.empty((B * H * W, 1, h, w), dtype=torch.float32, device=fmap1.device)
-              for (h, w) in _level_shapes(H, W, num_levels)]
+    with torch.cuda.device(fmap1.device):
+        mask = L.b200corr_allpairs_blocked_levels(num_levels, H, W, prec) if blocked and B > 0 else 0
+    shapes = _level_shapes(H, W, num_levels)
+    for l in range(num_levels):
+        if (mask >> l) & 1:
+            shapes[l] = blocked_level_dims(l, H, W)   # padded to whole 8x8 tiles
+    levels = [torch.empty((B * H * W, 1, h, w), dtype=torch.float32, device=fmap1.device) for (h, w) in shapes]
     nbytes = L.b200corr_allpairs_workspace_bytes(B, C, H, W, prec)
     ws = torch.empty((max(nbytes, 1) + 127) // 128 * 32, dtype=torch.float32, device=fmap1.device)
     with torch.cuda.device(fmap1.device):
-        mask = L.b200corr_allpairs_blocked_levels(num_levels, H, W, prec) if blocked and B > 0 else 0
         code = L.b200corr_allpairs_pyramid_layout(_lib.ptr(fmap1), _lib.ptr(fmap2), _lib.ptr_array(levels), num_levels,
                                                   B, C, H, W, H, W, 1.0 / math.sqrt(C), prec, mask, _lib.ptr(ws), nbytes,
                                                   _lib.current_stream(fmap1.device))
@@ -102,10 +107,18 @@ def allpairs_pyramid(fmap1, fmap2, num_levels=4, precision="tf32", blocked=False
     return (levels, mask) if blocked else levels
 
 
-def deblock(level):
-    """Row-major (Q, 1, H_l, W_l) copy of a level stored in the blocked layout."""
-    Q, _, h, w = level.shape
-    return level.view(Q, h // 8, w // 8, 8, 8).permute(0, 1, 3, 2, 4).reshape(Q, 1, h, w)
+def blocked_level_dims(level, H, W):
+    """(Hp, Wp) of a blocked level: the level's extent padded to whole 8x8 tiles (include/b200corr.h)."""
+    hp, wp = ctypes.c_int(), ctypes.c_int()
+    _lib.lib().b200corr_blocked_level_dims(level, H, W, ctypes.byref(hp), ctypes.byref(wp))
+    return hp.value, wp.value
+
+
+def deblock(level, h, w):
+    """Row-major (Q, 1, h, w) copy of a level stored in the blocked layout (padded to (Hp, Wp) = level.shape[2:])."""
+    Q, _, hp, wp = level.shape
+    full = level.view(Q, hp // 8, wp // 8, 8, 8).permute(0, 1, 3, 2, 4).reshape(Q, 1, hp, wp)
+    return full[:, :, :h, :w].contiguous()
 
 
 def lookup_forward(levels, coords, radius, H, W, mode="grid_sample", first_level=0, blocked_levels=0):
@@ -290,7 +303,8 @@ class _LookupFunction(torch.autograd.Function):
         if block._grad_levels is None:
             # the gradient pyramid is row-major whatever the layout of the forward volume (nothing in the
             # backward reads the forward volume)
-            block._grad_levels = [torch.zeros_like(v) for v in block._levels]
+            block._grad_levels = [v.new_zeros((v.shape[0], 1, h, w))
+                                  for v, (h, w) in zip(block._levels, _level_shapes(block.H, block.W, block.num_levels))]
         lookup_backward(block._grad_levels, coords, grad_out, block.radius, block.H, block.W, block.lookup_mode)
         return grad_out.new_zeros(1), None, None
 
@@ -347,7 +361,9 @@ class CorrBlock:
         if self._blocked == 0:
             return self._levels
         if self._rowmajor is None:
-            self._rowmajor = [deblock(v) if (self._blocked >> i) & 1 else v for i, v in enumerate(self._levels)]
+            shapes = _level_shapes(self.H, self.W, self.num_levels)
+            self._rowmajor = [deblock(v, *shapes[i]) if (self._blocked >> i) & 1 else v
+                              for i, v in enumerate(self._levels)]
         return self._rowmajor
 
     def get_corr_pyramid(self):
