@@ -146,6 +146,19 @@ int b200corr_warp_forward(const float *in, const float *flow, float *out, int B,
 int b200corr_warp_backward(const float *in, const float *flow, const float *grad_out, float *grad_in, float *grad_flow,
                            int B, int C, int H, int W, void *stream);
 
+/* ---------------------------------------------------------------- FlowNet2 natives
+ * Replace the reference's channelnorm_cuda / resample2d_cuda extensions
+ * (models/channelnorm_package/channelnorm_cuda.cc:6-27, models/resample2d_package/resample2d_cuda.cc:6-25): fp32, dense
+ * NCHW, outputs caller-owned.  norm_deg must be 2 and kernel_size 1 (what the reference uses; its kernels ignore
+ * norm_deg and read out of bounds for larger kernel sizes).  resample2d clamps the sampling corners to the image. */
+int b200corr_channelnorm_forward(const float *in, float *out, int B, int C, int H, int W, int norm_deg, void *stream);
+int b200corr_channelnorm_backward(const float *in, const float *out, const float *grad_out, float *grad_in, int B, int C,
+                                  int H, int W, int norm_deg, void *stream);
+int b200corr_resample2d_forward(const float *in, const float *flow, float *out, int B, int C, int H, int W,
+                                int kernel_size, int bilinear, void *stream);
+int b200corr_resample2d_backward(const float *in, const float *flow, const float *grad_out, float *grad_in,
+                                 float *grad_flow, int B, int C, int H, int W, int kernel_size, int bilinear, void *stream);
+
 /* ---------------------------------------------------------------- RAFT CorrBlock */
 
 /* Level l has shape (B*H*W, 1, H_l, W_l), H_0 = H, H_{l+1} = H_l / 2 (floor), same for W. */

@@ -6,6 +6,7 @@ TEST / BENCH INFRASTRUCTURE ONLY.  Sources are compiled where they lie under /ro
                                                        correlation_cuda_kernel.cu  (-DUSE_CUDA)
   oracle/_ref/ref_alt_cuda_corr/ref_alt_cuda_corr.so <- alt_cuda_corr/correlation.cpp +
                                                         correlation_kernel.cu
+  oracle/_ref/ref_resample2d_cuda/ref_resample2d_cuda.so <- resample2d_package/resample2d_cuda.cc + resample2d_kernel.cu
 They travel to the GPU box with the gpurun snapshot and are used there as
   * the "kernel to beat" timed beside ours by bench.py (never as the product path), and
   * a live pin of oracle/raft_oracle.alt_corr_* against the real alt_cuda_corr (tests -m gpu).
@@ -35,7 +36,7 @@ def so_path(name):
     return os.path.join(OUT, name, name + ".so")
 
 
-def build(which=("ref_sampler_cuda", "ref_alt_cuda_corr")):
+def build(which=("ref_sampler_cuda", "ref_alt_cuda_corr", "ref_resample2d_cuda")):
     if not os.path.isdir(REF):
         return
     cm = os.path.join(REF, "Pytorch-Correlation-extension/Correlation_Module")
@@ -47,6 +48,11 @@ def build(which=("ref_sampler_cuda", "ref_alt_cuda_corr")):
         ac = os.path.join(REF, "alt_cuda_corr")
         _load("ref_alt_cuda_corr", [f"{ac}/correlation.cpp", f"{ac}/correlation_kernel.cu"],
               ["-O3"], ["-O3"])
+    # FlowNet2's resample2d compiles unmodified against torch 2.11; channelnorm does not (its AT_DISPATCH takes the
+    # removed `tensor.type()` form, channelnorm_kernel.cu:111,152), so that op is pinned against its formula only
+    if "ref_resample2d_cuda" in which and not os.path.exists(so_path("ref_resample2d_cuda")):
+        rs = os.path.join(REF, "resample2d_package")
+        _load("ref_resample2d_cuda", [f"{rs}/resample2d_cuda.cc", f"{rs}/resample2d_kernel.cu"], ["-O3"], ["-O3"])
 
 
 def load_module(name):
@@ -62,6 +68,6 @@ def load_module(name):
 
 
 if __name__ == "__main__":
-    build(tuple(sys.argv[1:]) or ("ref_sampler_cuda", "ref_alt_cuda_corr"))
-    for n in ("ref_sampler_cuda", "ref_alt_cuda_corr"):
+    build(tuple(sys.argv[1:]) or ("ref_sampler_cuda", "ref_alt_cuda_corr", "ref_resample2d_cuda"))
+    for n in ("ref_sampler_cuda", "ref_alt_cuda_corr", "ref_resample2d_cuda"):
         print(n, os.path.exists(so_path(n)))

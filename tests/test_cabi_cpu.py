@@ -74,6 +74,11 @@ raft = importlib.import_module("models.raft.raft")           # models/raft/raft.
 assert raft.CorrBlock is b200.CorrBlock and raft.AlternateCorrBlock is b200.AlternateCorrBlock
 import alt_cuda_corr
 assert alt_cuda_corr.forward is b200.alt_cuda_corr.forward
+# FlowNet2's native wrappers (channelnorm.py:1, resample2d.py:1) import their extension modules by name
+cn = importlib.import_module("models.channelnorm_package.channelnorm")
+rs = importlib.import_module("models.resample2d_package.resample2d")
+from understanding_flow_robustness_b200 import flownet2_natives
+assert cn.channelnorm_cuda is flownet2_natives.channelnorm_cuda and rs.resample2d_cuda is flownet2_natives.resample2d_cuda
 print("shims ok")
 """ % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)

@@ -4,6 +4,7 @@ Public surface (same names / signatures as the reference's operator API):
   spatial_correlation_sample, SpatialCorrelationSampler, SpatialCorrelationSamplerFunction
       <- models/Pytorch-Correlation-extension/Correlation_Module/spatial_correlation_sampler/
   CorrBlock, AlternateCorrBlock, alt_cuda_corr            <- models/raft/corr.py, models/alt_cuda_corr/
+  ChannelNorm, Resample2d   FlowNet2's native ops  <- models/channelnorm_package, models/resample2d_package
   warp              PWC-Net's warp() (grid_sample of the map and of a ones mask, threshold, multiply) as one kernel
       <- models/PWCNet.py:164-204
   correlate_merge   correlate() -> LeakyReLU -> cat of the FlowNetC merge block as one kernel
@@ -32,6 +33,10 @@ def __getattr__(name):
         from . import merge_block
 
         return getattr(merge_block, name)
+    if name in ("ChannelNorm", "Resample2d", "ChannelNormFunction", "Resample2dFunction"):
+        from . import flownet2_natives
+
+        return getattr(flownet2_natives, name)
     if name == "warp":
         from .pwc_warp import warp
 

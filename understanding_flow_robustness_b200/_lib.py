@@ -24,6 +24,10 @@ PROTOTYPES = {
     "b200corr_merge_forward": (c_int, [c_void_p] * 3 + [c_int] * 8 + [c_float, c_void_p]),
     "b200corr_merge_backward_scratch_bytes": (c_size_t, [c_int] * 4),
     "b200corr_merge_backward": (c_int, [c_void_p] * 8 + [c_size_t] + [c_int] * 8 + [c_float, c_void_p]),
+    "b200corr_channelnorm_forward": (c_int, [c_void_p] * 2 + [c_int] * 5 + [c_void_p]),
+    "b200corr_channelnorm_backward": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
+    "b200corr_resample2d_forward": (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
+    "b200corr_resample2d_backward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "b200corr_warp_forward": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "b200corr_warp_backward": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "b200corr_allpairs_workspace_bytes": (c_size_t, [c_int] * 5),

@@ -19,6 +19,10 @@ def install_reference_shims(raft_package="models.raft"):
     sys.modules["spatial_correlation_sampler_backend"] = backend
     sys.modules["spatial_correlation_sampler"] = scs
     sys.modules["alt_cuda_corr"] = raft_corr.alt_cuda_corr
+    # FlowNet2's natives (models/channelnorm_package/channelnorm.py:1, models/resample2d_package/resample2d.py:1)
+    from . import flownet2_natives
+    sys.modules["channelnorm_cuda"] = flownet2_natives.channelnorm_cuda
+    sys.modules["resample2d_cuda"] = flownet2_natives.resample2d_cuda
     if raft_package:
         sys.modules[raft_package + ".corr"] = raft_corr
     return scs, raft_corr.alt_cuda_corr
