@@ -363,6 +363,37 @@ __device__ __forceinline__ void flush_row(const float *wrow, float *grow, int ox
   }
 }
 
+// schedulable 256-bit load (no volatile / memory clobber): the flush below puts all of a warp's sector loads in
+// flight before the first add -- the serialised load -> add -> store chain was 7.8 long_scoreboard stalls per issue
+__device__ __forceinline__ void ld256_sched(const float *p, float (&v)[8]) {
+  asm("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+      : "l"(p));
+}
+__device__ __forceinline__ void prefetch_l2(const float *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// which (window row r of this warp, sector g) pairs the flush touches, and their addresses
+template <int RPW, int WS>
+struct SectorPlan {
+  bool ok[RPW][3];
+  float *ptr[RPW][3];
+  __device__ __forceinline__ void make(float *slice, int warp, int oy, int ox, int LH, int LW, int ylo, int yhi, int clo,
+                                       int chi) {
+    const int c0 = ox & ~7, off = ox & 4;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int wr = warp * RPW + r, y = oy + wr;
+      const bool row_ok = wr < WS && wr >= ylo && wr <= yhi && y >= 0 && y < LH;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const int x = c0 + 8 * g;
+        ok[r][g] = row_ok && x >= 0 && x < LW && !(chi + off < 8 * g || clo + off >= 8 * g + 8);
+        ptr[r][g] = slice + (size_t)(row_ok ? y : 0) * LW + (ok[r][g] ? x : 0);
+      }
+    }
+  }
+};
+
 // Backward of the lookup (what autograd derives for grid_sample): the bilinear weights of every tap,
 // times its output gradient, are added into the query's own slice of the dense gradient pyramid.
 // Same decomposition as the forward kernel: CTA = 4 warps x 32 consecutive queries of one level,
@@ -394,6 +425,18 @@ lookup_bwd_kernel(const LookupParams p, const float *__restrict__ coords,
   const int slvl = lvl + p.first_level;   // coordinate scale of this level
   const int ox = window_origin<R>(cx, slvl, xlo, xhi), oy = window_origin<R>(cy, slvl, ylo, yhi);
   const int shift = path == PATH_SCALAR ? 0 : (ox & 3);
+  // the sectors of the gradient slice this warp will read-modify-write at the end: start them towards the L2 now,
+  // the tap tables and the gathering below hide the DRAM latency
+  float *const gslice = p.glvl[lvl] + ((size_t)b * p.HW + (q_ok ? q : 0)) * LH * LW;
+  if (path == PATH_SECTOR && q_ok) {
+    SectorPlan<RPW, WS> sp;
+    sp.make(gslice, warp, oy, ox, LH, LW, ylo, yhi, shift + xlo, shift + xhi);
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+        if (sp.ok[r][g]) prefetch_l2(sp.ptr[r][g]);
+  }
   const float smx = (float)(LW - 1), smy = (float)(LH - 1);
   const float ismx = __frcp_rn(smx), ismy = __frcp_rn(smy);
 #pragma unroll 1
@@ -490,8 +533,35 @@ lookup_bwd_kernel(const LookupParams p, const float *__restrict__ coords,
   if (!q_ok) return;
 
   // ---- add this warp's rows into the slice (only rows / sectors the taps can have touched)
-  float *slice = p.glvl[lvl] + ((size_t)b * p.HW + q) * LH * LW;
+  float *slice = gslice;
   const int clo = shift + xlo, chi = shift + xhi;
+  if (path == PATH_SECTOR) {
+    // all sector loads of this warp's rows first, then the adds and the stores
+    SectorPlan<RPW, WS> sp;
+    sp.make(slice, warp, oy, ox, LH, LW, ylo, yhi, clo, chi);
+    float v[RPW][3][8];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+        if (sp.ok[r][g]) ld256_sched(sp.ptr[r][g], v[r][g]);
+    const int off = ox & 4;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const float *wrow = wl + ((warp * RPW + r) * kCols) * 32;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        if (!sp.ok[r][g]) continue;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int sidx = 8 * g + k - off;
+          if (sidx >= 0 && sidx < kCols) v[r][g][k] += wrow[sidx * 32];
+        }
+        st256(sp.ptr[r][g], v[r][g]);
+      }
+    }
+    return;
+  }
 #pragma unroll 1
   for (int r = 0; r < RPW; ++r) {
     const int wr = warp * RPW + r, y = oy + wr;
