@@ -153,11 +153,11 @@ struct StageArgs {
 // Staged column 0 is level column (ox & ~3) for the vector flavours, ox itself for the scalar one.
 // Only the rows and the 32-byte sectors the taps touch are fetched; everything outside the slice is
 // staged as zero (= grid_sample's zero padding).
+// Two phases so that the tap tables (ALU work that needs only the coordinates) run while the loads are in flight:
+// stage_load issues every global load of this warp's rows into registers, stage_store parks them in the tile.
 template <int PATH, int NR, int WS>
-__device__ __forceinline__ void stage_rows(float *win, int lane, const StageArgs &a, int r0) {
+__device__ __forceinline__ void stage_load(const StageArgs &a, int r0, float (&v)[NR][24]) {
   constexpr int NL = PATH == PATH_SECTOR ? 24 : PATH == PATH_VEC4 ? 16 : 12;   // loaded
-  constexpr int NC = PATH == PATH_SCALAR ? 12 : 16;                            // staged
-  float v[NR][NL];
   // first loaded column: sector aligned / 16-byte aligned / exact
   const int c0 = PATH == PATH_SECTOR ? (a.ox & ~7) : PATH == PATH_VEC4 ? (a.ox & ~3) : a.ox;
   const bool hi4 = (a.ox & 4) != 0;  // PATH_SECTOR: staged column 0 is loaded column 4
@@ -193,6 +193,12 @@ __device__ __forceinline__ void stage_rows(float *win, int lane, const StageArgs
         if (row_ok && c0 + k >= 0 && c0 + k < a.LW) v[r][k] = __ldg(src + k);
     }
   }
+}
+
+template <int PATH, int NR, int WS>
+__device__ __forceinline__ void stage_store(float *win, int lane, const StageArgs &a, int r0, const float (&v)[NR][24]) {
+  constexpr int NC = PATH == PATH_SCALAR ? 12 : 16;                            // staged
+  const bool hi4 = (a.ox & 4) != 0;
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     float *dst = win + ((r0 + r) * kCols) * 32 + lane;
@@ -239,10 +245,11 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
   a.blocked = p.blocked[lvl] != 0;
   a.tiles_w = p.tiles_w[lvl];
 
-  // ---- stage this warp's rows (all of its loads are in flight together)
-  if (path == PATH_SECTOR) stage_rows<PATH_SECTOR, RPW, WS>(win, lane, a, warp * RPW);
-  else if (path == PATH_VEC4) stage_rows<PATH_VEC4, RPW, WS>(win, lane, a, warp * RPW);
-  else stage_rows<PATH_SCALAR, RPW, WS>(win, lane, a, warp * RPW);
+  // ---- this warp's window rows: all loads in flight together, parked in the tile after the tap tables
+  float sv[RPW][24];
+  if (path == PATH_SECTOR) stage_load<PATH_SECTOR, RPW, WS>(a, warp * RPW, sv);
+  else if (path == PATH_VEC4) stage_load<PATH_VEC4, RPW, WS>(a, warp * RPW, sv);
+  else stage_load<PATH_SCALAR, RPW, WS>(a, warp * RPW, sv);
   // ---- this warp's share of the 2N tap table entries
   const float smx = (float)(a.LW - 1), smy = (float)(a.LH - 1);
   const float ismx = __frcp_rn(smx), ismy = __frcp_rn(smy);
@@ -258,6 +265,9 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
     tab_r[e][lane] = rel;
     tab_a[e][lane] = frac;
   }
+  if (path == PATH_SECTOR) stage_store<PATH_SECTOR, RPW, WS>(win, lane, a, warp * RPW, sv);
+  else if (path == PATH_VEC4) stage_store<PATH_VEC4, RPW, WS>(win, lane, a, warp * RPW, sv);
+  else stage_store<PATH_SCALAR, RPW, WS>(win, lane, a, warp * RPW, sv);
   __syncthreads();
   if (!a.q_ok) return;
 
