@@ -1,5 +1,10 @@
-import os, sys, json
-sys.path.insert(0, "/root/repo")
+"""CorrBlock backward (B=4, 256x48x160, 12 lookups), five runs per layout with the number of cudaMallocs made inside the
+backward: 2.5 ms whenever the caching allocator serves the 1.25 GB gradient pyramid from its cache, 4-17 ms when it has to
+grow (GPU box)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from understanding_flow_robustness_b200 import CorrBlock, coords_grid
 B, C, H, W = 4, 256, 48, 160
