@@ -436,7 +436,9 @@ def test_full_size_raft_properties():
     ((1, 32, 24, 32), 4, "tf32", 3), ((1, 32, 16, 40), 3, "tf32", 3), ((1, 32, 16, 32), 4, "fp32", 0),
     # padded tiles: H not a multiple of 8, W / 2 not a multiple of 8 (FlyingThings 68x120, Sintel 55x128 shapes)
     ((1, 16, 68, 120), 4, "tf32", 3), ((1, 16, 55, 128), 4, "tf32", 3), ((2, 8, 13, 24), 3, "tf32", 3),
-    ((1, 8, 9, 8), 2, "tf32", 3), ((1, 8, 20, 36), 4, "tf32", 0)], ids=str)
+    ((1, 8, 9, 8), 2, "tf32", 3), ((1, 8, 20, 36), 4, "tf32", 0),
+    # more levels than the fused epilogue produces (levels >= 4 come from the pooling kernel), many queries per tile tail
+    ((1, 16, 32, 32), 5, "tf32", 3), ((3, 8, 24, 40), 4, "tf32x3", 3)], ids=str)
 def test_blocked_volume_layout_equals_rowmajor(shape, levels, precision, expect_mask):
     """The blocked layout (8x8 tiles of 64 floats, include/b200corr.h) is another element order of the same
     values: de-blocked levels and every lookup are bit-identical to the row-major kernels."""
