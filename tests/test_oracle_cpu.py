@@ -137,3 +137,37 @@ def test_warp_oracle_matches_reference_golden(path):
     np.testing.assert_array_equal(out.detach().numpy(), z["out"])
     np.testing.assert_allclose(gx.numpy(), z["gx"], rtol=0, atol=1e-6 * np.abs(z["gx"]).max())
     np.testing.assert_allclose(gf.numpy(), z["gflo"], rtol=0, atol=1e-6 * np.abs(z["gflo"]).max())
+
+
+def test_flownet2_oracle_against_torch_formulas():
+    """oracle/flownet2_oracle.py (restated from channelnorm_kernel.cu / resample2d_kernel.cu) against independent torch
+    formulas: the channel 2-norm and its gradient; resample2d == grid_sample(bilinear, padding_mode="border",
+    align_corners=True) at pixel + flow (clamping the four corners is border replication), forward and image gradient
+    (away from integer positions, where the reference's `xf - int(xf)` and floor agree for xf >= 0)."""
+    import torch
+
+    from oracle import flownet2_oracle as O
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((2, 3, 9, 11)).astype(np.float32)
+    g1 = rng.standard_normal((2, 1, 9, 11)).astype(np.float32)
+    t = torch.from_numpy(x).requires_grad_()
+    n = t.pow(2).sum(1, keepdim=True).sqrt()
+    n.backward(torch.from_numpy(g1))
+    out = O.channelnorm_forward(x)
+    np.testing.assert_allclose(out, n.detach().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(O.channelnorm_backward(x, out, g1), t.grad.numpy(), rtol=1e-5, atol=1e-7)
+
+    B, C, H, W = 2, 3, 9, 11
+    flow = (2.5 * rng.standard_normal((B, 2, H, W))).astype(np.float32)
+    flow[:, 0] = np.abs(flow[:, 0])           # xf, yf >= 0: truncation == floor in the backward weights
+    flow[:, 1] = np.abs(flow[:, 1])
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    gx = 2 * (xs[None] + flow[:, 0]) / (W - 1) - 1
+    gy = 2 * (ys[None] + flow[:, 1]) / (H - 1) - 1
+    grid = torch.from_numpy(np.stack([gx, gy], -1).astype(np.float32))
+    t = torch.from_numpy(x).requires_grad_()
+    ref = torch.nn.functional.grid_sample(t, grid, mode="bilinear", padding_mode="border", align_corners=True)
+    ref.backward(torch.from_numpy(g))
+    np.testing.assert_allclose(O.resample2d_forward(x, flow), ref.detach().numpy(), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(O.resample2d_backward(x, flow, g)[0], t.grad.numpy(), rtol=0, atol=2e-5)
