@@ -240,6 +240,28 @@ int b200corr_altcorr_backward(const float *fmap1, const float *fmap2, const floa
                               float *coords_grad, int B, int N, int H1, int W1, int H2, int W2,
                               int C, int radius, void *stream);
 
+/* ---------------------------------------------------------------- universal-patch placement */
+
+/* The host-side transform of the patch attack on the GPU.  Reference: patch_attacks/utils_patch.py:257-358
+ * (`circle_transform`: brightness jitter + clip, patch * mask, zoom, rotate, paste at a random location) and
+ * patch_attacks/main.py:537-542 (`adv = (1 - mask_canvas) * img + patch_canvas`).
+ * patch [3,p,p], mask [p,p], placements [n,5] = (scale, angle [rad], centre x, centre y, brightness offset),
+ * img1 / img2 / adv1 / adv2 (and the gradients below) [n,3,H,W] sharing the ELEMENT strides sN, sC, sH, sW
+ * (contiguous or channels_last):
+ *   q = clamp(patch + bright, 0, 1) * mask;  (u, v) = R(-angle) (x - cx, y - cy) / scale + (p-1)/2
+ *   adv_k = clamp((1 - bilinear(mask; u, v)) * img_k + bilinear(q; u, v), 0, 1)      zeros outside the patch */
+int b200corr_patch_compose_forward(const float *img1, const float *img2, const float *patch, const float *mask,
+                                   const float *placements, float *adv1, float *adv2, int n, int H, int W, int p,
+                                   long long sN, long long sC, long long sH, long long sW, void *stream);
+
+/* grad_patch [3,p,p] = d(<grad_adv1, adv1> + <grad_adv2, adv2>) / d patch, summed over the n pairs in index
+ * order (gather form, deterministic, no atomics).  scratch: b200corr_patch_compose_backward_scratch_bytes. */
+size_t b200corr_patch_compose_backward_scratch_bytes(int n, int p);
+int b200corr_patch_compose_backward(const float *img1, const float *img2, const float *patch, const float *mask,
+                                    const float *placements, const float *grad_adv1, const float *grad_adv2,
+                                    float *grad_patch, float *scratch, size_t scratch_bytes, int n, int H, int W, int p,
+                                    long long sN, long long sC, long long sH, long long sW, void *stream);
+
 /* ---------------------------------------------------------------- diagnostics */
 
 /* Runs `iters` dependent FP32 FMAs per thread on every SM and returns the achieved TFLOP/s in

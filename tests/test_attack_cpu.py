@@ -49,8 +49,8 @@ def _single(kind):
         pl = attack.sample_placements(6, 24, 32, p, cfg, torch.Generator().manual_seed(3)).double()
         with torch.no_grad():
             tgt = -net(i1, i2)
-        g, loss = attack.patch_gradient(net, i1, i2, patch, mask, patch.clone(), pl, tgt, 6, 0.1)
-        return g, loss
+        packed = attack.patch_gradient(net, i1, i2, patch, mask, patch.clone(), pl, tgt, 6, 0.1, attack.compose_torch)
+        return packed[:-1].view_as(patch), packed[-1]
     delta = torch.zeros(1, 2, 3, 24, 32).double()
     return attack.universal_perturbation_iteration(net, i1, i2, delta, 0.05, 0.01, 3, 6)
 
@@ -70,8 +70,8 @@ def _worker(rank, world, port, kind, q):
         pl = attack.sample_placements(6, 24, 32, p, cfg, torch.Generator().manual_seed(3)).double()[idx]
         with torch.no_grad():
             tgt = -net(i1[idx], i2[idx])
-        g, loss = attack.patch_gradient(net, i1[idx], i2[idx], patch, mask, patch.clone(), pl, tgt, 6, 0.1)
-        packed = torch.cat([g.reshape(-1), loss.reshape(1)])
+        packed = attack.patch_gradient(net, i1[idx], i2[idx], patch, mask, patch.clone(), pl, tgt, 6, 0.1,
+                                       attack.compose_torch)
         dist.all_reduce(packed)
         out = (packed[:-1].view_as(patch), packed[-1])
     else:
@@ -120,6 +120,26 @@ def test_placement_is_identity_for_centered_unit_patch():
     assert float(m.sum()) == pytest.approx(81.0, abs=1e-3)
 
 
+def test_brightness_column_shifts_and_clips_the_patch():
+    p, H, W = 9, 9, 9
+    patch = torch.rand(1, 3, p, p)
+    mask = torch.ones(1, 1, p, p)
+    pl = torch.tensor([[1.0, 0.0, (W - 1) / 2.0, (H - 1) / 2.0, 0.05], [1.0, 0.0, 4.0, 4.0, -2.0]])
+    canvas, _ = attack.place(patch, mask, pl, H, W)
+    assert torch.allclose(canvas[0], (patch[0] + 0.05).clamp(0, 1), atol=1e-5)
+    assert float(canvas[1].abs().max()) <= 1e-6                 # clipped at zero (utils_patch.py:272)
+
+
+def test_the_default_composition_refuses_cpu_tensors():
+    """No silent CPU path: the loops default to the CUDA kernel and say so when handed host tensors."""
+    net = TinyFlow()
+    i1, i2 = _data(2)
+    patch = torch.rand(1, 3, 10, 10)
+    cfg = attack.PatchAttackConfig()
+    with pytest.raises(RuntimeError):
+        attack.patch_attack_iteration(net, i1, i2, patch, attack.circle_mask(10), patch.clone(), cfg, 2)
+
+
 def test_patch_iteration_runs_and_keeps_range():
     net = TinyFlow()
     i1, i2 = _data(4)
@@ -127,6 +147,6 @@ def test_patch_iteration_runs_and_keeps_range():
     patch = torch.rand(1, 3, p, p)
     cfg = attack.PatchAttackConfig(lr=100.0, max_count=2)
     new, loss = attack.patch_attack_iteration(net, i1, i2, patch, attack.circle_mask(p), patch.clone(), cfg, 4,
-                                              torch.Generator().manual_seed(0))
+                                              torch.Generator().manual_seed(0), compose_fn=attack.compose_torch)
     assert new.shape == patch.shape and float(new.min()) >= 0.0 and float(new.max()) <= 1.0
     assert torch.isfinite(loss)

@@ -397,7 +397,7 @@ def test_full_size_raft_properties():
     B, C, H, W = 4, 256, 48, 160
     f1 = torch.randn(B, C, H, W, device="cuda")
     f2 = torch.randn(B, C, H, W, device="cuda")
-    blk = CorrBlock(f1, f2, num_levels=4, radius=4)
+    blk = CorrBlock(f1, f2, num_levels=4, radius=4, precision="tf32")
     pyr = blk.get_corr_pyramid()
     assert [tuple(v.shape) for v in pyr] == [(B * H * W, 1, 48, 160), (B * H * W, 1, 24, 80),
                                              (B * H * W, 1, 12, 40), (B * H * W, 1, 6, 20)]
@@ -479,3 +479,37 @@ def test_blocked_layout_with_autograd():
         assert blk._blocked == (3 if layout == "auto" else 0)
     for x, y in zip(*res):
         assert torch.equal(x, y)
+
+
+def test_corrblock_memory_is_released_by_refcount():
+    """The reference's pyramid dies with `corr_fn` (raft.py:150-156 keeps the only reference).  Ours must too:
+    no reference cycle block -> handle -> grad_fn -> ctx -> block, and an alive lookup graph must not pin the
+    1.25 GB forward volume (its backward never reads it)."""
+    import gc
+
+    from understanding_flow_robustness_b200 import CorrBlock, coords_grid
+    gc.collect()
+    gc.disable()
+    try:
+        torch.manual_seed(5)
+        B, C, H, W = 1, 64, 32, 64
+        f1 = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+        f2 = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+        c = coords_grid(B, H, W, "cuda") + torch.randn(B, 2, H, W, device="cuda")
+        torch.cuda.synchronize()
+        base = torch.cuda.memory_allocated()
+        blk = CorrBlock(f1, f2, 4, 4)
+        vol_bytes = sum(v.numel() * 4 for v in blk._levels)
+        assert torch.cuda.memory_allocated() - base >= vol_bytes
+        out = blk(c)
+        del blk                                              # graph (out) still alive: the volume must go anyway
+        assert torch.cuda.memory_allocated() - base < vol_bytes // 2
+        loss = out.square().mean()
+        loss.backward()
+        assert f1.grad is not None and float(f1.grad.abs().max()) > 0
+        del out, loss
+        f1.grad = f2.grad = None
+        torch.cuda.synchronize()
+        assert torch.cuda.memory_allocated() == base         # no gc.collect() happened
+    finally:
+        gc.enable()

@@ -85,6 +85,8 @@ FAST_CASES = [
     (3, 5, 9, 12, 9, 1),         # fewer channels than one chunk, several samples (a 3-D map would read the next sample)
     (2, 37, 10, 16, 21, 2),      # odd channel count on the patch-21 kernels
     (2, 130, 7, 12, 21, 2),      # C % 128 != 0 and C % 32 != 0: 32-channel backward units with a tail
+    (2, 256, 55, 128, 21, 2),    # BASELINE config 5: Sintel 436x1024 feature shape (odd H), full channel count
+    (2, 256, 68, 120, 21, 2),    # BASELINE config 5: FlyingThings 540x960 feature shape (W % 32 != 0)
 ]
 
 

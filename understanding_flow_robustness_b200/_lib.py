@@ -51,6 +51,10 @@ PROTOTYPES = {
     "b200corr_pyramid_backward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),
     "b200corr_altcorr_forward": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
     "b200corr_altcorr_backward": (c_int, [c_void_p] * 7 + [c_int] * 8 + [c_void_p]),
+    "b200corr_patch_compose_forward": (c_int, [c_void_p] * 7 + [c_int] * 4 + [ctypes.c_longlong] * 4 + [c_void_p]),
+    "b200corr_patch_compose_backward_scratch_bytes": (c_size_t, [c_int] * 2),
+    "b200corr_patch_compose_backward": (c_int, [c_void_p] * 9 + [c_size_t] + [c_int] * 4 + [ctypes.c_longlong] * 4
+                                        + [c_void_p]),
     "b200corr_measure_fp32_peak": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p]),
     "b200corr_measure_gather_peak": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, ctypes.POINTER(c_float), c_void_p]),
     "b200corr_launch_count": (ctypes.c_uint64, []),

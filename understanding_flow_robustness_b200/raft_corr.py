@@ -12,9 +12,10 @@ layout and channel order) and the pybind surface of models/alt_cuda_corr/correla
   alt_cuda_corr.backward(fmap1, fmap2, coords, corr_grad, radius) -> [fmap1_grad, fmap2_grad, coords_grad]
 
 Differences from the reference, all deliberate:
-  * the volume is computed from TF32-rounded features by default (`precision="tf32"`; bound in
-    DESIGN.md); `precision="tf32x3"` runs the split-TF32 contraction (fp32-level accuracy, still on the
-    tensor cores), `precision="fp32"` the exact CUDA-core kernel;
+  * the volume is contracted on the tensor cores: `precision="tf32x3"` (default) is the split-TF32
+    contraction with the accuracy of the reference's fp32 matmul, `precision="tf32"` one TF32 pass (half
+    the build time; bound in DESIGN.md), `precision="fp32"` the exact CUDA-core kernel; the environment
+    variable B200CORR_VOLUME_PRECISION picks the default for callers that cannot pass arguments;
   * both blocks are differentiable w.r.t. the feature maps (the reference's AlternateCorrBlock is
     forward-only because nothing wraps alt_cuda_corr.backward); coordinates get no gradient, as in
     the reference (raft.py:188 detaches them, correlation_kernel.cu:307 returns zeros);
@@ -23,6 +24,7 @@ Differences from the reference, all deliberate:
 """
 import ctypes
 import math
+import os
 import types
 
 import torch
@@ -179,6 +181,21 @@ def pyramid_backward(grad_levels, B, H, W):
     _lib.check(code, "b200corr_pyramid_backward")
 
 
+def volume_backward(gvol, fmap1, fmap2, scale, precision):
+    """dF1 = scale * gvol . F2^T, dF2 = scale * gvol^T . F1 for gvol (B*HW, 1, H, W): what autograd derives for
+    `torch.matmul(fmap1^T, fmap2)` (models/raft/corr.py:104) -- in the precision the volume was built with."""
+    B, C, H, W = fmap1.shape
+    g = gvol.view(B, H * W, H * W)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = precision == "tf32"
+    try:
+        g1 = torch.bmm(fmap2.reshape(B, C, H * W), g.transpose(1, 2)).mul_(scale).view_as(fmap1)
+        g2 = torch.bmm(fmap1.reshape(B, C, H * W), g).mul_(scale).view_as(fmap2)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return g1, g2
+
+
 # ------------------------------------------------------------------------------------------------
 # alt_cuda_corr drop-in (models/alt_cuda_corr/correlation.cpp:23-54)
 def _alt_check(fmap1, fmap2, coords):
@@ -251,6 +268,19 @@ class _AltCorrFunction(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+class _GradState:
+    """What the backward of a CorrBlock needs, and nothing that references the block, its pyramid or the
+    autograd handle: the graph (handle -> grad_fn -> ctx) must not keep the 1.25 GB volume alive, nor form a
+    cycle with the block (the reference's pyramid is freed by refcount when `corr_fn` goes out of scope)."""
+
+    __slots__ = ("B", "H", "W", "num_levels", "radius", "lookup_mode", "precision", "grad_levels")
+
+    def __init__(self, B, H, W, num_levels, radius, lookup_mode, precision):
+        self.B, self.H, self.W, self.num_levels = B, H, W, num_levels
+        self.radius, self.lookup_mode, self.precision = radius, lookup_mode, precision
+        self.grad_levels = None
+
+
 class _VolumeFunction(torch.autograd.Function):
     """Builds the pyramid into `block` and returns a 1-element handle that carries the autograd edge
     from the lookups back to the feature maps."""
@@ -259,38 +289,28 @@ class _VolumeFunction(torch.autograd.Function):
     def forward(ctx, fmap1, fmap2, block):
         block._build(fmap1, fmap2)
         ctx.save_for_backward(fmap1, fmap2)
-        ctx.block = block
+        ctx.state = block._state
         return fmap1.new_zeros(1)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, _grad_handle):
         fmap1, fmap2 = ctx.saved_tensors
-        block = ctx.block
+        st = ctx.state
         B, C, H, W = fmap1.shape
-        gl = block._grad_levels
-        block._grad_levels = None
+        gl = st.grad_levels
+        st.grad_levels = None
         if gl is None:
             return torch.zeros_like(fmap1), torch.zeros_like(fmap2), None
         pyramid_backward(gl, B, H, W)
-        gvol = gl[0].view(B, H * W, H * W)
-        scale = 1.0 / math.sqrt(C)
-        # plain library GEMMs (cuBLAS): dF1 = scale * F2 gvol^T, dF2 = scale * F1 gvol -- in the precision
-        # the volume itself was built with (TF32 tensor cores for "tf32", exact fp32 for "fp32")
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = block.precision == "tf32"
-        try:
-            g1 = torch.bmm(fmap2.reshape(B, C, H * W), gvol.transpose(1, 2)).mul_(scale).view_as(fmap1)
-            g2 = torch.bmm(fmap1.reshape(B, C, H * W), gvol).mul_(scale).view_as(fmap2)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
+        g1, g2 = volume_backward(gl[0], fmap1, fmap2, 1.0 / math.sqrt(C), st.precision)
         return g1, g2, None
 
 
 class _LookupFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, handle, coords, block):
-        ctx.block = block
+        ctx.state = block._state
         ctx.save_for_backward(coords)
         return lookup_forward(block._levels, coords, block.radius, block.H, block.W, block.lookup_mode,
                               blocked_levels=block._blocked)
@@ -299,34 +319,42 @@ class _LookupFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         (coords,) = ctx.saved_tensors
-        block = ctx.block
-        if block._grad_levels is None:
+        st = ctx.state
+        if st.grad_levels is None:
             # the gradient pyramid is row-major whatever the layout of the forward volume (nothing in the
             # backward reads the forward volume)
-            block._grad_levels = [v.new_zeros((v.shape[0], 1, h, w))
-                                  for v, (h, w) in zip(block._levels, _level_shapes(block.H, block.W, block.num_levels))]
-        lookup_backward(block._grad_levels, coords, grad_out, block.radius, block.H, block.W, block.lookup_mode)
+            st.grad_levels = [grad_out.new_zeros((st.B * st.H * st.W, 1, h, w))
+                              for (h, w) in _level_shapes(st.H, st.W, st.num_levels)]
+        lookup_backward(st.grad_levels, coords, grad_out, st.radius, st.H, st.W, st.lookup_mode)
         return grad_out.new_zeros(1), None, None
 
 
 class CorrBlock:
     """models/raft/corr.py:26-106."""
 
-    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, compute_spatial=False, precision="tf32",
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, compute_spatial=False, precision=None,
                  lookup_mode="grid_sample", layout="auto"):
-        """layout: "auto" keeps the two fine levels in the blocked layout (8x8 tiles, include/b200corr.h) where the
+        """precision: "tf32x3" (default: split-TF32 on the tensor cores, the accuracy of the reference's fp32
+        matmul), "tf32" (one TF32 pass, half the build time, |err| <= 2^-10 * sum|f1 f2| / sqrt(C)) or "fp32"
+        (CUDA cores).  None reads the environment variable B200CORR_VOLUME_PRECISION, so a caller that cannot
+        pass arguments (the unmodified models/raft/raft.py:150-156) can still choose.
+        layout: "auto" keeps the two fine levels in the blocked layout (8x8 tiles, include/b200corr.h) where the
         library supports the problem -- the lookups read them 1.4x faster; `corr_pyramid` / `get_corr_pyramid()`
         still hand out the reference's row-major tensors (converted on first use).  "rowmajor": as the reference."""
         self.num_levels = num_levels
         self.radius = radius
         self.compute_spatial = compute_spatial
+        if precision is None:
+            precision = os.environ.get("B200CORR_VOLUME_PRECISION", "tf32x3")
+        if precision not in PRECISIONS:
+            raise ValueError(f"CorrBlock: precision must be one of {sorted(PRECISIONS)}")
         self.precision = precision
         self.lookup_mode = lookup_mode
         if layout not in ("auto", "rowmajor"):
             raise ValueError("CorrBlock: layout must be 'auto' or 'rowmajor'")
         self._want_blocked = layout == "auto"
         self._levels, self._blocked, self._rowmajor = [], 0, None
-        self._grad_levels = None
+        self._state = None
         self._handle = None
         if self.compute_spatial:
             # corr.py:33-54: FlowNetC-style 21x21 (dilation 2) correlation instead of all pairs
@@ -342,6 +370,7 @@ class CorrBlock:
                 self._levels.append(corr)
         else:
             self.B, self.C, self.H, self.W = fmap1.shape
+            self._state = _GradState(self.B, self.H, self.W, num_levels, radius, lookup_mode, precision)
             needs_grad = torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad)
             if needs_grad:
                 self._handle = _VolumeFunction.apply(fmap1.contiguous(), fmap2.contiguous(), self)
@@ -390,7 +419,7 @@ class CorrBlock:
                               blocked_levels=self._blocked)
 
     @staticmethod
-    def corr(fmap1, fmap2, precision="tf32"):
+    def corr(fmap1, fmap2, precision="tf32x3"):
         """corr.py:98-106 -> (B, H, W, 1, H, W)."""
         B, C, H, W = fmap1.shape
         return allpairs_pyramid(fmap1, fmap2, 1, precision)[0].view(B, H, W, 1, H, W)
