@@ -14,8 +14,14 @@ carries RAFT corr+lookup ms/iter (config 3) under "raft".
               measured in this run (the path is FP32-pipe bound); in-bounds FLOPs
   cpu_baseline / --impl reference : the reference's own CPU extension (oracle/_ref, compiled from
               correlation.cpp) on the host cores, bounded sample, scaled to pairs/s
-N > 1 (torchrun): weak scaling, every rank its own batch of 8 pairs, no data-path collective
-(the correlation is independent per image pair); barrier + max-over-ranks timing.
+N > 1 (torchrun): the headline stays the sampler line (weak scaling, every rank its own batch of 8 pairs, no
+data-path collective -- SURVEY.md 8e: the correlation is independent per image pair; barrier +
+max-over-ranks timing).  The metric of the path that HAS a collective is in the same line and repeated in
+its last key `summary` (so a truncated tail still carries it):
+  attack                 : BASELINE config 4, universal 100x100 patch, global batch 64 sharded r::N (strong
+                           scaling), 120 KB gradient all-reduce (NCCL) per inner step, >= 20 timed iterations
+  universal_perturbation : global_attacks/universal_perturbation.py loop, batch 64 at 256x640, 3.9 MB all-reduce
+  nccl_value_check       : N-rank all-reduced gradients == rank 0's single-process gradients of the same batch
 """
 import argparse
 import json
@@ -72,11 +78,19 @@ class ClockSampler:
         while self.proc is not None and not self.samples and time.perf_counter() - t0 < timeout:
             time.sleep(0.05)
 
+    def close(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
     def stop(self, t0, t1):
+        r = self.window(t0, t1)
+        self.close()
+        return r
+
+    def window(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
-        self.proc.terminate()
         mhz, mx, reasons = [], None, set()
         for (t, line) in self.samples:
             if t < t0 or t > t1 + 0.1:
@@ -96,7 +110,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------- reference CPU arm
-def reference_cpu_pairs_per_s(steps, warmup, budget_s=2.5):
+def reference_cpu_pairs_per_s(steps, warmup, budget_s=2.5, exact_config1=False):
     """Times the reference's own CPU path (oracle/_ref, else the C oracle port) on all host cores.
 
     A step is the bench workload (batch 8, 48x160, patch 21, dilation 2) at a reduced channel count
@@ -151,22 +165,38 @@ def reference_cpu_pairs_per_s(steps, warmup, budget_s=2.5):
     t = sum(ts) / len(ts)
     pairs_per_s = B / (t * CFG["C"] / Cs)
     sample = (f"batch {B} x {Cs} of {CFG['C']} channels x {H}x{W} fwd+bwd per step "
-              f"({Cs}/{CFG['C']} of the MACs, time scaled x{CFG['C'] // Cs}); {steps} steps, mean")
-    return pairs_per_s, t * 1e3, {"value": pairs_per_s, "unit": "pairs/s", "cores": cores, "kind": kind,
-                                  "sample": sample}
+              f"({Cs}/{CFG['C']} of the MACs, time EXTRAPOLATED x{CFG['C'] // Cs}: the CPU loops are linear in C, "
+              f"correlation.cpp:20-35); {steps} steps, mean")
+    cb = {"value": pairs_per_s, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample,
+          "channel_subsample": {"channels_timed": Cs, "channels_workload": CFG["C"], "time_scaled_by": CFG["C"] // Cs}}
+    if exact_config1:
+        # BASELINE config 1 exactly (B=1, C=256): no extrapolation.  The backward parallelises over the batch
+        # only (correlation.cpp:148-149), so at B=1 it runs on ONE thread whatever the core count.
+        g = torch.Generator().manual_seed(1)
+        a = torch.randn(1, CFG["C"], H, W, generator=g)
+        b = torch.randn(1, CFG["C"], H, W, generator=g)
+        t0 = time.perf_counter()
+        out = fwd(a, b)
+        t1 = time.perf_counter()
+        bwd(a, b, torch.ones(tuple(out.shape)))
+        t2 = time.perf_counter()
+        cb["config1_exact"] = {"what": f"(1,{CFG['C']},{H},{W}) patch 21 dilation_patch 2, one forward + one backward, not extrapolated",
+                               "fwd_s": t1 - t0, "bwd_s": t2 - t1, "pairs_per_s": 1.0 / (t2 - t0),
+                               "threads": {"fwd": cores, "bwd": 1}}
+    return pairs_per_s, t * 1e3, cb
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, ms, cb = reference_cpu_pairs_per_s(max(1, args.steps), max(0, args.warmup))
+    v, ms, cb = reference_cpu_pairs_per_s(max(1, args.steps), max(0, args.warmup), exact_config1=True)
     line = {"impl": "reference", "metric": "FlowNetC corr fwd+bwd pairs/s", "value": v, "unit": "pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args.gpus), "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "channel_subsample": cb["channel_subsample"], "config1_exact": cb.get("config1_exact")}
     _emit(line)
 
 
@@ -229,6 +259,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-attack", action="store_true")
     ap.add_argument("--attack-batch", type=int, default=64)
+    ap.add_argument("--attack-iters", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -343,14 +374,25 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    clk = clocks.window(t_wall0, t_wall1) if rank == 0 else None
     # FP32 FFMA peak (the roofline denominator), measured right behind the timed region: same clocks,
     # same power / thermal state as the kernels it is compared with (measured after the attack bench it
     # read 65.8 instead of 72.6 TFLOP/s on one box: the power cap of a GPU that had just run the conv stack)
     import ctypes
     pk = ctypes.c_float()
-    _lib.check(L.b200corr_measure_fp32_peak(4000, ctypes.byref(pk), _lib.current_stream(dev)), "fp32 peak")
-    peak = float(pk.value)
+    t_p0 = time.perf_counter()
+    peaks_seen = []
+    while time.perf_counter() - t_p0 < 0.45 or not peaks_seen:      # long enough for two 200 ms clock samples
+        _lib.check(L.b200corr_measure_fp32_peak(4000, ctypes.byref(pk), _lib.current_stream(dev)), "fp32 peak")
+        peaks_seen.append(float(pk.value))
+    t_p1 = time.perf_counter()
+    peaks_seen.sort()
+    peak = peaks_seen[len(peaks_seen) // 2]
+    peak_clk = None
+    if rank == 0:
+        pc = clocks.stop(t_p0, t_p1)
+        peak_clk = {"sm_mhz": pc.get("sm_mhz"), "reasons": pc.get("reasons"), "probe_runs": len(peaks_seen),
+                    "tflops_min_median_max": [peaks_seen[0], peak, peaks_seen[-1]]}
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
 
@@ -417,11 +459,14 @@ def main():
     del pipe
     os.sched_setaffinity(0, all_cpus)   # the CPU baseline below uses every host core
 
-    attack_res = None
+    attack_res = pert_res = nccl_res = None
     if not args.no_attack:
         del h_sets
         torch.cuda.empty_cache()
-        attack_res = attack_bench(dev, rank, world, args.attack_batch)
+        attack_res = attack_bench(dev, rank, world, args.attack_batch, args.attack_iters)
+        pert_res = perturbation_bench(dev, rank, world, args.attack_batch)
+        if world > 1:
+            nccl_res = nccl_check_bench(dev, rank, world, args.attack_batch)
 
     if rank != 0:
         if world > 1:
@@ -442,7 +487,9 @@ def main():
             traffic = None
     roofline = {"bound": "fp32_fma", "kernel": "sampler_bwd_kernel (2 launches/step)", "achieved": ach,
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-                "peak_source": "FP32 FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                "peak_source": "FP32 FFMA micro-benchmark measured in this run right behind the timed region "
+                               "(MEASURED_PEAKS.json has no FP32 figure); median of the probe runs",
+                "peak_probe_clocks": peak_clk,
                 "flops_counted": "in-bounds MACs x2 (dense count is 1.369x larger)",
                 "step": {"fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
                          "fwd_frac": flop_launch / (fwd_ms * 1e-3) / 1e12 / peak,
@@ -451,7 +498,7 @@ def main():
     line = {"metric": "FlowNetC corr fwd+bwd pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world), timed_loop=timed_loop), "clocks": clk,
+            "config": workload_config(world), "timed_loop": timed_loop, "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pcie_roof": e2e_roof, "frac_of_pcie_roof": e2e_value / world / e2e_roof["pairs_per_s"],
                     "how": "pinned host in1/in2/grad_out -> device -> fwd+bwd -> pinned host out/grad_in1/grad_in2, every step; "
@@ -460,6 +507,14 @@ def main():
 
     if attack_res is not None:
         line["attack"] = attack_res
+        line["universal_perturbation"] = pert_res
+        if nccl_res is not None:
+            line["nccl_value_check"] = nccl_res
+    if not args.no_raft and world == 1:
+        try:
+            line["reference_cuda"] = reference_cuda_bench(dev)
+        except Exception as e:
+            line["reference_cuda"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if not args.no_raft:
         line["raft"] = raft_bench(dev)
         try:
@@ -473,62 +528,33 @@ def main():
         except Exception as e:  # never lose the GPU numbers to a host-side problem
             line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "unavailable",
                                     "sample": f"{type(e).__name__}: {e}"}
+    # last key: the numbers a truncated tail must still carry (<= 300 bytes)
+    summ = {"n_gpus": world, "corr_pairs_s": round(value, 1), "roofline_step": round(roofline["step"]["fwd_bwd_frac"], 3)}
+    if attack_res is not None:
+        summ.update(attack_iters_s=round(attack_res["value"], 3), attack_allreduce_B=attack_res["allreduce_bytes"],
+                    pert_iters_s=round(pert_res["value"], 3), pert_allreduce_B=pert_res["allreduce_bytes"])
+    if nccl_res is not None:
+        summ["nccl_check_ok"] = nccl_res.get("ok")
+    if "raft" in line:
+        summ.update(raft_ms_iter=round(line["raft"]["ms_per_iter"], 4), raft_roofline=round(line["raft"]["roofline"]["frac"], 3))
+    line["summary"] = summ
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def attack_bench(dev, rank, world, global_batch):
-    """BASELINE config 4: universal 100x100 patch attack on the FlowNetC harness (random init), global
-    batch of 384x1280 pairs sharded r::G over the ranks, patch gradient all-reduced (NCCL) every inner
-    step.  Strong scaling: the global batch is fixed.  iteration = clean forward + max_count x
-    (forward + backward) + all-reduce + update."""
+def _timed_iters(fn, iters, dev, world, sync_each=False):
+    """CUDA-event time of `iters` calls of fn, barrier + synchronize on both sides, MAX over ranks -> ms per call."""
     import torch
     import torch.distributed as dist
 
-    from understanding_flow_robustness_b200 import attack
-    from understanding_flow_robustness_b200.harness import FlowNetCHarness
-    torch.manual_seed(0)                                   # same weights / patch on every rank
-    net = FlowNetCHarness().to(dev).eval().to(memory_format=torch.channels_last)   # cuDNN's preferred conv layout
-    for q in net.parameters():
-        q.requires_grad_(False)
-    H, W, p = 384, 1280, 100
-    idx = attack.shard_slice(global_batch, rank, world)
-    g = torch.Generator(device=dev).manual_seed(100 + rank)
-    i1 = torch.rand(len(idx), 3, H, W, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
-    i2 = torch.rand(len(idx), 3, H, W, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
-    patch = torch.rand(1, 3, p, p, device=dev)
-    mask = attack.circle_mask(p, dev)
-    cfg = attack.PatchAttackConfig()
-    init = patch.clone()
-
-    def it(pt):
-        return attack.patch_attack_iteration(net, i1, i2, pt, mask, init, cfg, global_batch, g)[0]
-
-    # BASELINE config 2 on the way: whole-network forward+backward pairs/s of this rank's shard
-    def net_step():
-        a = i1[:8].clone().requires_grad_(True)
-        net(a, i2[:8]).mean().backward()
-    net_step()
-    torch.cuda.synchronize()
-    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0.record()
-    for _ in range(3):
-        net_step()
-    n1.record()
-    torch.cuda.synchronize()
-    net_pairs_per_s = min(8, len(idx)) * 3 / (n0.elapsed_time(n1) * 1e-3)
-
-    patch = it(patch)                                      # warm-up (cuDNN autotune, allocator)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    iters = 3
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        patch = it(patch)
+        fn()
     e1.record()
     if world > 1:
         dist.barrier()
@@ -536,15 +562,297 @@ def attack_bench(dev, rank, world, global_batch):
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / iters
-    return {"metric": "patch-attack iters/s", "value": 1e3 / ms, "unit": "iters/s", "ms_per_iter": ms,
-            "pairs_per_s": global_batch * 1e3 / ms, "scaling": "strong", "global_batch": global_batch,
-            "pairs_per_rank": len(idx), "n_gpus": world,
-            "config": "FlowNetC harness (random init) 384x1280, 100x100 circular patch, max_count 2, cosine loss, "
-                      "patch-gradient all-reduce (NCCL) per inner step",
-            "allreduce_bytes": int(patch.numel() * 4 + 4),
-            "flownetc_fwd_bwd_pairs_per_s_per_gpu": net_pairs_per_s,
-            "flownetc_config": "BASELINE config 2: FlowNetC harness random init, forward+backward, 384x1280, batch 8, 1 GPU"}
+    return float(t.item()) / iters
+
+
+def attack_bench(dev, rank, world, global_batch, iters=20):
+    """BASELINE config 4: universal 100x100 patch attack on FlowNetC (random init), global batch of 384x1280
+    pairs sharded r::G over the ranks, patch gradient all-reduced (NCCL) every inner step.  Strong scaling: the
+    global batch is fixed.  iteration = clean forward + max_count x (compose + forward + backward + all-reduce
+    + update).
+
+    Network: the reference's own models/FlowNetC.py through the shims where its file is present (row
+    `reference_body`, eager), and the same network (same weights: state_dict copied) with the merge block on the
+    fused kernel -- the headline row, its per-rank work (clean forward; gradient step) replayed from CUDA graphs
+    so the ~600 launches per step cost no host time; the all-reduce and the update stay eager between replays."""
+    import torch
+    import torch.distributed as dist
+
+    from understanding_flow_robustness_b200 import attack
+    from understanding_flow_robustness_b200.harness import FlowNetCHarness, reference_models
+    torch.manual_seed(0)                                   # same weights / patch on every rank
+    fmt = torch.channels_last                              # cuDNN's preferred conv layout
+    net = FlowNetCHarness(fused_merge=True).to(dev).eval().to(memory_format=fmt)
+    for q in net.parameters():
+        q.requires_grad_(False)
+    H, W, p = 384, 1280, 100
+    idx = attack.shard_slice(global_batch, rank, world)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    i1 = torch.rand(len(idx), 3, H, W, device=dev, generator=g).contiguous(memory_format=fmt)
+    i2 = torch.rand(len(idx), 3, H, W, device=dev, generator=g).contiguous(memory_format=fmt)
+    patch0 = torch.rand(1, 3, p, p, device=dev)
+    mask = attack.circle_mask(p, dev)
+    cfg = attack.PatchAttackConfig()
+
+    # BASELINE config 2 on the way: whole-network forward+backward pairs/s on 8 pairs of this rank's shard
+    nb = min(8, len(idx))
+
+    def net_step():
+        a = i1[:nb].clone().requires_grad_(True)
+        net(a, i2[:nb]).mean().backward()
+    net_step()
+    net_ms = _timed_iters(net_step, 5, dev, 1)
+    net_pairs_per_s = nb / (net_ms * 1e-3)
+
+    # ---- headline: graph-replayed per-rank work
+    target = torch.empty(len(idx), 2, H, W, device=dev)
+    s_patch = patch0.clone()
+    s_pl = attack.sample_placements(len(idx), H, W, p, cfg, g, dev)
+
+    def clean_fn(a, b):
+        with torch.no_grad():
+            return -net(a, b)
+
+    def grad_fn(pt, pl):
+        return attack.patch_gradient(net, i1, i2, pt, mask, patch0, pl, target, global_batch, cfg.alpha)
+
+    how = "cuda-graph replay of the per-rank work (clean forward; gradient step), all-reduce + update eager"
+    try:
+        g_clean = attack.GraphedGradient(clean_fn, [i1, i2])
+        g_grad = attack.GraphedGradient(grad_fn, [s_patch, s_pl])
+    except Exception as e:                               # capture unavailable: time the eager loop
+        torch.cuda.synchronize()
+        how = f"eager (graph capture failed: {type(e).__name__}: {e})"[:200]
+        g_clean = lambda: clean_fn(i1, i2)                # noqa: E731
+        g_grad = grad_fn
+    state = {"patch": patch0.clone(), "loss": None}
+
+    def iteration():
+        target.copy_(g_clean())
+        pl = attack.sample_placements(len(idx), H, W, p, cfg, g, dev)
+        pt = state["patch"]
+        for _ in range(cfg.max_count):
+            packed = g_grad(pt, pl)
+            if world > 1:
+                dist.all_reduce(packed)                   # the one collective of the path (NCCL over NVLink)
+            pt, state["loss"] = attack.apply_patch_step(pt, packed, cfg)
+        state["patch"] = pt
+
+    for _ in range(2):
+        iteration()
+    ms = _timed_iters(iteration, iters, dev, world)
+    res = {"metric": "patch-attack iters/s", "value": 1e3 / ms, "unit": "iters/s", "ms_per_iter": ms, "iters_timed": iters,
+           "pairs_per_s": global_batch * 1e3 / ms, "scaling": "strong", "global_batch": global_batch,
+           "pairs_per_rank": len(idx), "n_gpus": world, "timed_loop": how,
+           "config": "FlowNetC (reference parameters, random init, merge block on the fused kernel) 384x1280, 100x100 "
+                     "circular patch placed by the compose kernel, max_count 2, cosine loss, patch-gradient all-reduce "
+                     "(NCCL) per inner step",
+           "allreduce_bytes": int(patch0.numel() * 4 + 4), "allreduces_per_iter": cfg.max_count,
+           "final_loss": float(state["loss"]),
+           "flownetc_fwd_bwd_pairs_per_s_per_gpu": net_pairs_per_s,
+           "flownetc_config": f"BASELINE config 2: FlowNetC random init, forward+backward, 384x1280, batch {nb}, 1 GPU, eager"}
+    del g_clean, g_grad
+    # ---- same loop, eager, fused network (what the graph replaces) and on the reference's unmodified FlowNetC.py
+    def eager_iter(model):
+        def it():
+            state["patch"] = attack.patch_attack_iteration(model, i1, i2, state["patch"], mask, patch0, cfg,
+                                                           global_batch, g)[0]
+        return it
+    it = eager_iter(net)
+    it()
+    res["eager_ms_per_iter"] = _timed_iters(it, 5, dev, world)
+    if reference_models.available():
+        try:
+            # the reference's memory format (contiguous NCHW): its correlate() hands conv3's output to the
+            # operator as is, and the operator -- like the reference's, CHECK_CONTIGUOUS -- refuses channels_last
+            ref = reference_models.reference_flownetc().to(dev).eval()
+            ref.load_state_dict(net.state_dict())
+            for q in ref.parameters():
+                q.requires_grad_(False)
+            j1, j2 = i1.contiguous(), i2.contiguous()
+
+            def it():
+                state["patch"] = attack.patch_attack_iteration(ref, j1, j2, state["patch"], mask, patch0, cfg,
+                                                               global_batch, g)[0]
+            it()
+            rms = _timed_iters(it, 5, dev, world)
+            res["reference_body"] = {"what": "the reference's UNMODIFIED models/FlowNetC.py (correlate() -> this package's "
+                                             "sampler through the shims), same weights, eager, NCHW", "ms_per_iter": rms,
+                                     "iters_per_s": 1e3 / rms, "tree": reference_models.reference_root()}
+            del ref, j1, j2
+        except Exception as e:
+            res["reference_body"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    else:
+        res["reference_body"] = {"error": "reference model files not staged (baseline/stage_reference.py)"}
+    del net
+    torch.cuda.empty_cache()
+    return res
+
+
+def perturbation_bench(dev, rank, world, global_batch, iters=5):
+    """global_attacks/universal_perturbation.py:452-530, batched and pair-sharded: batch 64 at the reference's
+    training resolution 256x640, n_step 10 (its default), learning rate 2e-3, sign steps; the (2,3,256,640)
+    gradient (3.9 MB) is all-reduced every step.  iteration = clean forward + n_step x (forward + backward +
+    all-reduce + update)."""
+    import torch
+    import torch.distributed as dist
+
+    from understanding_flow_robustness_b200 import attack
+    from understanding_flow_robustness_b200.harness import FlowNetCHarness
+    torch.manual_seed(0)
+    fmt = torch.channels_last
+    net = FlowNetCHarness(fused_merge=True).to(dev).eval().to(memory_format=fmt)
+    for q in net.parameters():
+        q.requires_grad_(False)
+    H, W, n_step, lr, eps = 256, 640, 10, 2e-3, 0.02
+    idx = attack.shard_slice(global_batch, rank, world)
+    g = torch.Generator(device=dev).manual_seed(200 + rank)
+    i1 = torch.rand(len(idx), 3, H, W, device=dev, generator=g).contiguous(memory_format=fmt)
+    i2 = torch.rand(len(idx), 3, H, W, device=dev, generator=g).contiguous(memory_format=fmt)
+    target = torch.empty(len(idx), 2, H, W, device=dev)
+    s_delta = torch.zeros(1, 2, 3, H, W, device=dev)
+
+    def clean_fn(a, b):
+        with torch.no_grad():
+            return -net(a, b)
+
+    def grad_fn(d):
+        return attack.perturbation_gradient(net, i1, i2, d, target, global_batch)
+
+    how = "cuda-graph replay of the per-rank work, all-reduce + update eager"
+    try:
+        g_clean = attack.GraphedGradient(clean_fn, [i1, i2])
+        g_grad = attack.GraphedGradient(grad_fn, [s_delta])
+    except Exception as e:
+        torch.cuda.synchronize()
+        how = f"eager (graph capture failed: {type(e).__name__}: {e})"[:200]
+        g_clean = lambda: clean_fn(i1, i2)                # noqa: E731
+        g_grad = grad_fn
+    state = {"delta": torch.zeros_like(s_delta), "loss": None}
+
+    def iteration():
+        target.copy_(g_clean())
+        d = state["delta"]
+        for _ in range(n_step):
+            packed = g_grad(d)
+            if world > 1:
+                dist.all_reduce(packed)
+            d, state["loss"] = attack.apply_perturbation_step(d, packed, eps, lr)
+        state["delta"] = d
+
+    iteration()
+    ms = _timed_iters(iteration, iters, dev, world)
+    out = {"metric": "universal-perturbation iters/s", "value": 1e3 / ms, "unit": "iters/s", "ms_per_iter": ms,
+           "iters_timed": iters, "pairs_per_s": global_batch * 1e3 / ms, "scaling": "strong",
+           "global_batch": global_batch, "pairs_per_rank": len(idx), "n_gpus": world, "timed_loop": how,
+           "allreduce_bytes": int(s_delta.numel() * 4 + 4), "allreduces_per_iter": n_step,
+           "final_loss": float(state["loss"]), "delta_linf": float(state["delta"].abs().max()),
+           "config": f"FlowNetC (fused merge block) {H}x{W}, delta (2,3,{H},{W}), n_step {n_step}, lr {lr}, eps {eps}, "
+                     "I-FGSM sign steps, cosine loss"}
+    del net, g_clean, g_grad
+    torch.cuda.empty_cache()
+    return out
+
+
+def nccl_check_bench(dev, rank, world, global_batch):
+    """All-reduced N-rank gradients of the bench's global batch == rank 0's single-process gradients."""
+    import torch
+
+    from understanding_flow_robustness_b200 import attack
+    from understanding_flow_robustness_b200.harness import FlowNetCHarness
+    torch.manual_seed(0)
+    net = FlowNetCHarness(fused_merge=True).to(dev).eval()
+    for q in net.parameters():
+        q.requires_grad_(False)
+    res = attack.nccl_value_check(net, dev, rank, world, global_pairs=global_batch, H=384, W=1280, p=100)
+    # the same check in fp64 (sampler's fp64 kernels, torch-op placement) on a small batch: pins the plumbing to 1e-9
+    net64 = FlowNetCHarness(fused_merge=False).to(dev).eval().double()
+    r64 = attack.nccl_value_check(net64, dev, rank, world, global_pairs=2 * world, H=64, W=128, p=16, dtype=torch.float64)
+    res["fp64"] = r64
+    if rank == 0:
+        res["ok"] = bool(res["ok"] and r64["ok"])
+    del net, net64
+    torch.cuda.empty_cache()
+    return res
+
+
+def reference_cuda_bench(dev):
+    """The reference's own CUDA kernels, compiled unmodified for sm_100a (oracle/_ref, built by
+    oracle/build_ref_cuda.py), timed on this GPU next to ours: the kernels to beat.  Never on the product path."""
+    import math
+
+    import torch
+    import torch.nn.functional as F
+
+    from oracle import build_ref_cuda
+    from understanding_flow_robustness_b200 import backend
+    out = {}
+
+    def timeit(fn, n, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    B, C, H, W, P = CFG["B"], CFG["C"], CFG["H"], CFG["W"], CFG["patch"]
+    torch.manual_seed(0)
+    a = torch.randn(B, C, H, W, device=dev)
+    b = torch.randn(B, C, H, W, device=dev)
+    g = torch.randn(B, P, P, H, W, device=dev)
+    try:
+        ref = build_ref_cuda.load_module("ref_sampler_cuda")
+        rf = timeit(lambda: ref.forward(a, b, *Q), 3)
+        rb = timeit(lambda: ref.backward(a, b, g, *Q), 2)
+        of = timeit(lambda: backend.forward(a, b, *Q), 20, 3)
+        ob = timeit(lambda: backend.backward(a, b, g, *Q), 20, 3)
+        o, r = backend.forward(a, b, *Q), ref.forward(a, b, *Q)
+        out["sampler"] = {"config": f"({B},{C},{H},{W}) patch 21 dilation_patch 2", "reference_fwd_ms": rf,
+                          "reference_bwd_ms": rb, "ours_fwd_ms": of, "ours_bwd_ms": ob, "speedup_fwd": rf / of,
+                          "speedup_bwd": rb / ob, "speedup_fwd_bwd": (rf + rb) / (of + ob),
+                          "max_rel_diff_fwd": float((o - r).abs().max() / r.abs().max())}
+        del o, r
+    except Exception as e:
+        out["sampler"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    del a, b, g
+    try:
+        ref_alt = build_ref_cuda.load_module("ref_alt_cuda_corr")
+        from understanding_flow_robustness_b200 import AlternateCorrBlock, coords_grid
+        c = RAFT_CFG
+        Bq, Cq, Hq, Wq = c["B"], c["C"], c["H"], c["W"]
+        f1 = torch.randn(Bq, Cq, Hq, Wq, device=dev)
+        f2 = torch.randn(Bq, Cq, Hq, Wq, device=dev)
+        coords = coords_grid(Bq, Hq, Wq, dev) + 3.0 * torch.randn(Bq, 2, Hq, Wq, device=dev)
+        with torch.no_grad():
+            f1n = f1.permute(0, 2, 3, 1).contiguous()
+            pyr2 = [f2]
+            for _ in range(3):
+                pyr2.append(F.avg_pool2d(pyr2[-1], 2, stride=2))
+            f2n = [q.permute(0, 2, 3, 1).contiguous() for q in pyr2]
+            cn = coords.permute(0, 2, 3, 1)
+
+            def ref_alt_iter():          # models/raft/corr.py:120-137
+                outs = []
+                for i in range(4):
+                    ci = (cn / 2 ** i).reshape(Bq, 1, Hq, Wq, 2).contiguous()
+                    (c_,) = ref_alt.forward(f1n, f2n[i], ci, 4)
+                    outs.append(c_.squeeze(1))
+                return torch.stack(outs, 1).reshape(Bq, -1, Hq, Wq) / math.sqrt(Cq)
+            r_alt = timeit(ref_alt_iter, 2)
+            alt = AlternateCorrBlock(f1, f2, 4, 4)
+            o_alt = timeit(lambda: alt(coords), 5)
+            pure = AlternateCorrBlock(f1, f2, 4, 4, dense_max_keys=0)
+            o_pure = timeit(lambda: pure(coords), 5)
+        out["alt_cuda_corr"] = {"config": f"B={Bq}, {Cq}x{Hq}x{Wq}, 4 levels, radius 4, one lookup", "reference_ms_per_iter": r_alt,
+                                "ours_ms_per_iter": o_alt, "ours_pure_alt_kernel_ms_per_iter": o_pure,
+                                "speedup": r_alt / o_alt, "speedup_pure_alt_kernel": r_alt / o_pure}
+    except Exception as e:
+        out["alt_cuda_corr"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    return out
 
 
 def merge_bench(dev):
@@ -621,7 +929,7 @@ def raft_bench(dev):
 
     def build():
         blk[0] = None   # RAFT holds one block per forward: the previous 1.25 GB pyramid is released first
-        blk[0] = CorrBlock(f1, f2, c["levels"], c["radius"])
+        blk[0] = CorrBlock(f1, f2, c["levels"], c["radius"], precision="tf32")
 
     def lookups():
         for cc in coords:
@@ -646,22 +954,12 @@ def raft_bench(dev):
         build()   # an eager pyramid for the lookups below (the captured one lives in the graph's pool)
         look_fn, how_look = graphed(lookups)
         look_ms = timed(look_fn, 5) / c["iters"]
-        # the gather ceiling of the memory system on the lookup's own access pattern: one 10-row x 64-byte
-        # window per query slice of pyramid level 0, nothing else (b200corr_measure_gather_peak)
-        import ctypes
-
-        from understanding_flow_robustness_b200 import _lib
-        lvl0 = blk[0]._levels[0]   # (the probe only needs the memory region: layout-agnostic)
-        gr = ctypes.c_float(0.0)
-        _lib.check(_lib.lib().b200corr_measure_gather_peak(_lib.ptr(lvl0), B * H * W, H * W * 4, W * 4,
-                                                           ctypes.byref(gr), _lib.current_stream(dev)), "gather peak")
-        gather_grows = float(gr.value)
         # the same two numbers with the reference's row-major volume layout (layout="rowmajor")
         rm = [None]
 
         def build_rm():
             rm[0] = None
-            rm[0] = CorrBlock(f1, f2, c["levels"], c["radius"], layout="rowmajor")
+            rm[0] = CorrBlock(f1, f2, c["levels"], c["radius"], precision="tf32", layout="rowmajor")
 
         def lookups_rm():
             for cc in coords:
@@ -676,6 +974,7 @@ def raft_bench(dev):
         rm[0] = None
         build()
         layout_mask = blk[0]._blocked
+        from understanding_flow_robustness_b200 import raft_corr
         alt = AlternateCorrBlock(f1, f2, c["levels"], c["radius"])
         alt_ms = timed(lambda: alt(coords[0]), 3)
         # the same block with every level on the alt_cuda_corr kernel (the reference's structure), with level 1
@@ -685,6 +984,22 @@ def raft_bench(dev):
             a2 = AlternateCorrBlock(f1, f2, c["levels"], c["radius"], dense_max_keys=dmk)
             alt_rows[name + "_ms_per_iter"] = timed(lambda: a2(coords[0]), 3)
             del a2
+        # alt_cuda_corr.backward at level 0 (the path's backward scatter): f1 gradient in registers, f2 gradient by atomics
+        f1n = f1.permute(0, 2, 3, 1).contiguous()
+        f2n = f2.permute(0, 2, 3, 1).contiguous()
+        cn = coords[0].permute(0, 2, 3, 1).reshape(B, 1, H, W, 2).contiguous()
+        cg = torch.randn(B, 1, 81, H, W, device=dev)
+        ab_ms = timed(lambda: raft_corr.alt_cuda_corr.backward(f1n, f2n, cn, cg, c["radius"]), 5)
+        af_ms = timed(lambda: raft_corr.alt_cuda_corr.forward(f1n, f2n, cn, c["radius"]), 5)
+        alt_bytes = B * H * W * (81 * 4 + 2 * C * 4 + 100 * C * 4 * 2)     # grad read + f1 r/w + window read + RMW
+        alt_rows["alt_cuda_corr_level0"] = {
+            "forward_ms": af_ms, "backward_ms": ab_ms,
+            "forward_tflops": 2.0 * B * H * W * 100 * C / (af_ms * 1e-3) / 1e12,
+            "backward_tflops": 4.0 * B * H * W * 100 * C / (ab_ms * 1e-3) / 1e12,
+            "backward_scatter_gbs": alt_bytes / (ab_ms * 1e-3) / 1e9,
+            "what": "one level-0 call (B,1,H,W,2) coords; scatter bytes = every window pixel's C floats read once and "
+                    "read-modify-written once (L2 atomics), + f1, f1_grad, corr_grad"}
+        del f1n, f2n, cn, cg
         alt_rows["block_init_ms"] = timed(lambda: AlternateCorrBlock(f1, f2, c["levels"], c["radius"]), 3)
         alt_rows["dense_levels_from"] = alt._dense_from
         alt_rows["dense_bytes"] = int(sum(v.numel() * 4 for v in alt._dense))
@@ -725,15 +1040,10 @@ def raft_bench(dev):
                                "bytes": "volume + 3 pooled levels written once + features read once"},
             "roofline_lookup": {"bound": "hbm", "achieved": look_bytes / (look_ms * 1e-3) / 1e9, "peak": hbm,
                                 "unit": "GB/s", "frac": look_bytes / (look_ms * 1e-3) / 1e9 / hbm, "peak_source": src,
-                                "bytes": "324-channel output written + 4 levels x 10x10 window read per query",
-                                # a lookup is a gather of 10-row windows, one DRAM access per window row:
-                                # rows/s against the gather-only ceiling measured in this run
-                                "gather": {"achieved": B * HW * c["levels"] * 10 / (look_ms * 1e-3) / 1e9,
-                                           "peak": gather_grows, "unit": "1e9 window rows/s",
-                                           "frac": B * HW * c["levels"] * 10 / (look_ms * 1e-3) / 1e9 / max(gather_grows, 1e-9),
-                                           "peak_source": "b200corr_measure_gather_peak on pyramid level 0 in this run "
-                                                          "(level-0 slices only: every row is a DRAM access; the kernel's "
-                                                          "coarse levels partly hit in L2)"}}}
+                                "bytes": "324-channel output written + 4 levels x 10x10 window read per query"},
+            "roofline": {"bound": "hbm", "what": "(build + 12 lookups) / 12 against the algorithmic bytes of both at the HBM copy peak",
+                         "bound_ms_per_iter": (vol_bytes + c["iters"] * look_bytes) / (hbm * 1e9) * 1e3 / c["iters"],
+                         "frac": (vol_bytes + c["iters"] * look_bytes) / (hbm * 1e9) * 1e3 / (build_ms + c["iters"] * look_ms)}}
 
 
 if __name__ == "__main__":

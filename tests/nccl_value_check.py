@@ -20,11 +20,14 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     net = FlowNetCHarness(fused_merge=True).to(dev).eval()
-    res = attack.nccl_value_check(net, dev, rank, world, global_pairs=2 * world, H=128, W=192, p=32)
+    res32 = attack.nccl_value_check(net, dev, rank, world, global_pairs=2 * world, H=128, W=192, p=32)
+    net64 = FlowNetCHarness(fused_merge=False).to(dev).eval().double()
+    res64 = attack.nccl_value_check(net64, dev, rank, world, global_pairs=2 * world, H=64, W=128, p=16, dtype=torch.float64)
     dist.barrier()
     if rank == 0:
-        print(res)
-        assert res["ok"], res
+        print(res32)
+        print(res64)
+        assert res32["ok"] and res64["ok"], (res32, res64)
         print("nccl value check ok")
     dist.destroy_process_group()
 

@@ -130,8 +130,18 @@ def test_universal_perturbation_at_256x640_sharded_equals_whole_batch():
     for r in range(2):
         idx = attack.shard_slice(n, r, 2)
         parts += attack.perturbation_gradient(net, i1[idx], i2[idx], delta, tgt[idx], n)
-    assert float((parts[:-1] - whole[:-1]).abs().max()) <= 1e-4 * float(whole[:-1].abs().max())
+    # fp32: cuDNN picks other algorithms (summation orders) for batch 2 than for batch 4 and the cosine-loss gradient
+    # of a random-init net is a sum of nearly cancelling terms -> 1e-2 here; the fp64 run below pins the arithmetic
+    assert float((parts[:-1] - whole[:-1]).abs().max()) <= 1e-2 * float(whole[:-1].abs().max())
     assert abs(float(parts[-1]) - float(whole[-1])) <= 1e-5 * abs(float(whole[-1]))
+    net64 = _net().double()
+    a, b, d64 = i1[:, :, :64, :128].double(), i2[:, :, :64, :128].double(), delta[..., :64, :128].double()
+    with torch.no_grad():
+        t64 = -net64(a, b)
+    whole64 = attack.perturbation_gradient(net64, a, b, d64, t64, n)
+    parts64 = sum(attack.perturbation_gradient(net64, a[i], b[i], d64, t64[i], n)
+                  for i in (attack.shard_slice(n, r, 2) for r in range(2)))
+    assert float((parts64 - whole64).abs().max()) <= 1e-9 * float(whole64.abs().max())
     eps, lr = 0.02, 0.005
     new, loss = attack.universal_perturbation_iteration(net, i1, i2, torch.zeros_like(delta), eps, lr, 3, n)
     assert new.shape == delta.shape and torch.isfinite(loss)

@@ -418,7 +418,7 @@ def test_full_size_raft_properties():
         assert float((pyr[l][: 2 * H * W] - ref).abs().max()) <= 1e-5
     # lookup at integer coordinates (direct mode) returns volume entries exactly
     c = coords_grid(B, H, W, "cuda")
-    out = CorrBlock(f1, f2, 4, 4, lookup_mode="direct")(c)
+    out = CorrBlock(f1, f2, 4, 4, precision="tf32", lookup_mode="direct")(c)
     assert out.shape == (B, 324, H, W)
     centre = out[:, 4 * 9 + 4]                      # level 0, zero offset
     diag = pyr[0].view(B, H * W, H * W).diagonal(dim1=1, dim2=2).reshape(B, H, W)

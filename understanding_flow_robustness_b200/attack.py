@@ -208,36 +208,44 @@ class GraphedGradient:
         return self.out
 
 
-def nccl_value_check(flow_fn, device, rank, world, global_pairs, H, W, p, tol=1e-4, group=None):
+def nccl_value_check(flow_fn, device, rank, world, global_pairs, H, W, p, tol=None, group=None, dtype=torch.float32):
     """SURVEY section 4 item 6 as a function: every rank computes the patch gradient and the universal-perturbation
     gradient of its shard (pairs r::G of ONE seeded global batch) and all-reduces them (NCCL); rank 0 also computes
     both gradients of the whole batch in a single autograd call.  Returns the relative max-norm differences.
-    Library convolutions run in fp32 (no TF32) for the duration of the check."""
+    Library convolutions run in fp32 (no TF32) for the duration of the check.
+
+    dtype float64 (flow_fn in double; the sampler's fp64 kernels, torch-op placement) pins the plumbing to 1e-9;
+    in float32 cuDNN picks other algorithms -- other summation orders -- for a shard than for the whole batch, and
+    the gradients are sums of nearly cancelling terms: default tolerance 1e-2 there."""
+    if tol is None:
+        tol = 1e-9 if dtype == torch.float64 else 1e-2
+    compose_fn = compose_cuda if dtype == torch.float32 else compose_torch
     prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
         g = torch.Generator(device=device).manual_seed(1234)       # same stream of numbers on every rank
-        i1 = torch.rand(global_pairs, 3, H, W, device=device, generator=g)
-        i2 = torch.rand(global_pairs, 3, H, W, device=device, generator=g)
-        patch = torch.rand(1, 3, p, p, device=device, generator=g)
-        mask = circle_mask(p, device)
+        i1 = torch.rand(global_pairs, 3, H, W, device=device, generator=g).to(dtype)
+        i2 = torch.rand(global_pairs, 3, H, W, device=device, generator=g).to(dtype)
+        patch = torch.rand(1, 3, p, p, device=device, generator=g).to(dtype)
+        mask = circle_mask(p, device).to(dtype)
         cfg = PatchAttackConfig()
-        pl = sample_placements(global_pairs, H, W, p, cfg, g, device)
-        delta = 0.01 * torch.randn(1, 2, 3, H, W, device=device, generator=g)
+        pl = sample_placements(global_pairs, H, W, p, cfg, g, device).to(dtype)
+        delta = (0.01 * torch.randn(1, 2, 3, H, W, device=device, generator=g)).to(dtype)
         idx = shard_slice(global_pairs, rank, world)
         with torch.no_grad():
             tgt = -flow_fn(i1[idx], i2[idx])
-        gp = patch_gradient(flow_fn, i1[idx], i2[idx], patch, mask, patch, pl[idx], tgt, global_pairs, 0.0)
+        gp = patch_gradient(flow_fn, i1[idx], i2[idx], patch, mask, patch, pl[idx], tgt, global_pairs, 0.0, compose_fn)
         gd = perturbation_gradient(flow_fn, i1[idx], i2[idx], delta, tgt, global_pairs)
         _allreduce_sum(gp, group)
         _allreduce_sum(gd, group)
         res = {"world": world, "global_pairs": global_pairs, "image": [H, W], "patch": p, "tol": tol,
+               "dtype": str(dtype).replace("torch.", ""),
                "allreduce_bytes": {"patch": gp.numel() * 4, "perturbation": gd.numel() * 4}}
         if rank == 0:
             with torch.no_grad():
                 tgt_all = -flow_fn(i1, i2)
-            wp = patch_gradient(flow_fn, i1, i2, patch, mask, patch, pl, tgt_all, global_pairs, 0.0)
+            wp = patch_gradient(flow_fn, i1, i2, patch, mask, patch, pl, tgt_all, global_pairs, 0.0, compose_fn)
             wd = perturbation_gradient(flow_fn, i1, i2, delta, tgt_all, global_pairs)
 
             def rel(a, b):

@@ -71,7 +71,8 @@ class FlowNetCHarness(nn.Module):
         self.register_buffer("mean", torch.tensor(self.MEAN, dtype=torch.float64).view(1, 3, 1, 1), persistent=False)
 
     def features(self, x):
-        a1 = self.conv1((x - self.mean).float())    # normalize_correctly: double mean, cast back (:72-79,92-93)
+        # normalize_correctly: double mean, cast back (:72-79,92-93; `.float()` there -- the weights' dtype here)
+        a1 = self.conv1((x - self.mean).to(self.conv1[0].weight.dtype))
         a2 = self.conv2(a1)
         return a2, self.conv3(a2)
 
