@@ -65,7 +65,13 @@ altcorr_fwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2,
 
   // one window row at a time (a real loop: the fully unrolled 100-pixel version thrashed the
   // instruction cache): WN coalesced pixel reads, then the row's partial dot products are reduced
-  // across lanes through the per-warp tile (lane l < WN sums column l)
+  // across lanes through the per-warp tile (lane l < WN sums column l).
+  // Measured in round 2 (scripts/time_altcorr.py, B=4, 48x160, C=256): the kernel is bound by L2->L1 bytes, not
+  // by latency or L1 hits -- branch-free rows with all 2*WN loads issued first: 0.24 ms vs 0.22 ms per level
+  // (the skipped out-of-range pixels now cost bandwidth); a __syncthreads per window row to keep the 8 queries'
+  // shared lines in L1: 0.221 vs 0.212 ms; a CTA-wide staging of the union window box in shared memory
+  // (8x8 query blocks, 8-channel chunks, cp.async double buffer): 0.31 ms (bank conflicts of the 32-byte
+  // pixel slices + two barriers per chunk).  None kept.
 #pragma unroll 1
   for (int iy = 0; iy < G::WN; ++iy) {
     const int y2 = fy - R + iy;
@@ -159,28 +165,41 @@ altcorr_bwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2,
       GS[warp][idx] = g;
     }
     __syncwarp();
-    for (int idx = 0; idx < G::NW; ++idx) {
-      const int iy = idx / G::WN, ix = idx - iy * G::WN;
-      const int y2 = fy - R + iy, x2 = fx - R + ix;
-      const float g = GS[warp][idx];
-      if (g == 0.f || y2 < 0 || y2 >= H2 || x2 < 0 || x2 >= W2) continue;
-      const size_t off = (((size_t)b * H2 + y2) * W2 + x2) * C;
-      const float4 *p2 = reinterpret_cast<const float4 *>(f2 + off);
-      float *g2 = f2g + off;
+#pragma unroll 1
+    for (int iy = 0; iy < G::WN; ++iy) {
+      const int y2 = fy - R + iy;
+      if (y2 < 0 || y2 >= H2) continue;        // warp-uniform
+      const size_t rowoff = (((size_t)b * H2 + y2) * W2) * C;
+      // all loads of the window row first (clamped addresses, 2*WN in flight per lane), then the FMAs and the
+      // vector reductions
+      float4 v[G::WN][NV];
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        if (lane + 32 * i < nvec) {
-          const float4 v = __ldg(p2 + lane + 32 * i);
-          ga[i].x = fmaf(g, v.x, ga[i].x);
-          ga[i].y = fmaf(g, v.y, ga[i].y);
-          ga[i].z = fmaf(g, v.z, ga[i].z);
-          ga[i].w = fmaf(g, v.w, ga[i].w);
-          float *d = g2 + 4 * (lane + 32 * i);
-          atomicAdd(d, g * a[i].x);
-          atomicAdd(d + 1, g * a[i].y);
-          atomicAdd(d + 2, g * a[i].z);
-          atomicAdd(d + 3, g * a[i].w);
-        }
+      for (int ix = 0; ix < G::WN; ++ix) {
+        const int x2 = min(max(fx - R + ix, 0), W2 - 1);
+        const float4 *p2 = reinterpret_cast<const float4 *>(f2 + rowoff + (size_t)x2 * C);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[ix][i] = __ldg(p2 + min(lane + 32 * i, nvec - 1));
+      }
+#pragma unroll
+      for (int ix = 0; ix < G::WN; ++ix) {
+        const int x2 = fx - R + ix;
+        const float g = GS[warp][iy * G::WN + ix];
+        if (g == 0.f || x2 < 0 || x2 >= W2) continue;
+        float *g2 = f2g + rowoff + (size_t)x2 * C;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (lane + 32 * i < nvec) {
+            ga[i].x = fmaf(g, v[ix][i].x, ga[i].x);
+            ga[i].y = fmaf(g, v[ix][i].y, ga[i].y);
+            ga[i].z = fmaf(g, v[ix][i].z, ga[i].z);
+            ga[i].w = fmaf(g, v[ix][i].w, ga[i].w);
+            // one 16-byte vector reduction per lane (sm_90+) instead of four scalar atomics
+            float *d = g2 + 4 * (lane + 32 * i);
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(g * a[i].x), "f"(g * a[i].y),
+                         "f"(g * a[i].z), "f"(g * a[i].w)
+                         : "memory");
+          }
+      }
     }
   }
   float4 *o = reinterpret_cast<float4 *>(f1g + ((size_t)b * HW1 + q) * C);
