@@ -212,6 +212,23 @@ int b200corr_lookup_forward_from(const float *const *h_levels, int num_levels, i
                                  const float *coords, float *out, int B, int H, int W, int radius, int mode,
                                  void *stream);
 
+/* ---- lookup fused with the motion encoder's first convolution.
+ * Reference: corr = corr_fn(coords1) (models/raft/raft.py:189) followed by cor = F.relu(self.convc1(corr))
+ * (models/raft/update.py:104,111; convc1 = Conv2d(L*(2r+1)^2, n_out, 1)).  The (B, L*(2r+1)^2, H, W) lookup
+ * result is never materialised: out[B, n_out, H, W] = act(sum_k W[:, k] * lookup[:, k] + bias), act = ReLU if
+ * `relu`.  Samples and weights are rounded to TF32, accumulation in fp32 (torch's default for this convolution:
+ * torch.backends.cudnn.allow_tf32).
+ * prepare: weight [n_out, L*(2r+1)^2] (the conv weight with its 1x1 spatial dims dropped) -> wprep, once per
+ * weight update; wprep holds b200corr_lookup_convc1_weight_bytes bytes, 16-byte aligned.
+ * forward: levels / blocked_levels / coords / mode as b200corr_lookup_forward_layout (first_level 0);
+ * n_out a multiple of 32, <= 256; bias [n_out] or NULL. */
+size_t b200corr_lookup_convc1_weight_bytes(int num_levels, int radius, int n_out);
+int b200corr_lookup_convc1_prepare(const float *weight, float *wprep, int num_levels, int radius, int n_out,
+                                   void *stream);
+int b200corr_lookup_convc1_forward(const float *const *h_levels, int num_levels, int blocked_levels,
+                                   const float *coords, const float *wprep, const float *bias, float *out, int B,
+                                   int H, int W, int radius, int mode, int n_out, int relu, void *stream);
+
 /* Accumulates (+=) d(out)/d(level l) into h_grad_levels[l] (caller zero-initialises once per
  * CorrBlock; several lookups of the same block accumulate).  Coordinates get no gradient
  * (the reference detaches them, models/raft/raft.py:188). */

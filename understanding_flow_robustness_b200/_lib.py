@@ -46,6 +46,10 @@ PROTOTYPES = {
                                         c_int, c_int, c_int, c_void_p]),
     "b200corr_lookup_forward_from": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                              c_int, c_int, c_int, c_void_p]),
+    "b200corr_lookup_convc1_weight_bytes": (c_size_t, [c_int] * 3),
+    "b200corr_lookup_convc1_prepare": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200corr_lookup_convc1_forward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                               c_void_p] + [c_int] * 7 + [c_void_p]),
     "b200corr_lookup_backward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_int,
                                          c_int, c_int, c_int, c_void_p]),
     "b200corr_pyramid_backward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),

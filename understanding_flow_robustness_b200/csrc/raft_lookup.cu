@@ -32,182 +32,10 @@
 // volume -- same CTA / lane mapping as the forward, each warp owning three window rows, so neither
 // shared nor global atomics are needed (see lookup_bwd_kernel).  Coordinates get no gradient
 // (raft.py:188 detaches them).
-#include "common.cuh"
+#include "raft_lookup.cuh"
 
 namespace {
-
-constexpr int kMaxLevels = 8;
-constexpr int QT = 32;  // queries per CTA
-
-struct LookupParams {
-  const float *lvl[kMaxLevels];
-  float *glvl[kMaxLevels];
-  int LH[kMaxLevels], LW[kMaxLevels];
-  int path[kMaxLevels];  // access flavour per level (sector / 16-byte / scalar), from width and alignment
-  int num_levels, B, HW, radius, mode;
-  int blocked[kMaxLevels];   // forward only: the level is stored as 8x8 tiles of 64 floats (b200corr.h)
-  int tiles_w[kMaxLevels];   // blocked levels: tiles per row of the padded slice
-  long long slice[kMaxLevels];   // floats per query slice (LH * LW, or the padded size of a blocked level)
-  int first_level;   // pyramid level of list entry 0: entry i has extent (H, W) >> (first_level + i), coordinate scale 2^-(first_level + i)
-};
-
-template <int R>
-struct Geo {
-  static constexpr int N = 2 * R + 1;      // taps per axis
-  static constexpr int WS = 2 * R + 4;     // window per axis: the taps + one guard row/column on either side
-};
-
-// 256-bit / 128-bit read-only loads that do not pollute L1 (every sector is used exactly once)
-__device__ __forceinline__ void ldg256(const float *p, float (&v)[8]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void ldg128(const float *p, float (&v)[4]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
-               : "l"(p));
-}
-
-// grid_sample's accumulation nw*w + ne*w + sw*w + se*w with the contraction pinned, so that the
-// fast and the general sampling loop (and ATen's own FMA-contracted kernel) agree bit for bit
-__device__ __forceinline__ float bilerp(float c00, float c01, float c10, float c11, float ax, float bx,
-                                        float ay, float by) {
-  float v = __fmul_rn(c00, __fmul_rn(bx, by));
-  v = __fmaf_rn(c01, __fmul_rn(ax, by), v);
-  v = __fmaf_rn(c10, __fmul_rn(bx, ay), v);
-  return __fmaf_rn(c11, __fmul_rn(ax, ay), v);
-}
-
-// a / b correctly rounded from y = RN(1/b) (Markstein: q = RN(a*y), r = a - b*q exactly by FMA,
-// RN(q + r*y) is the correctly rounded quotient for every b whose significand is not all ones --
-// b is a small integer here).  Zero, non-finite and huge operands take the IEEE routine.
-__device__ __forceinline__ float div_by(float a, float b, float y) {
-  if (!(fabsf(a) < 1e30f) || !(b >= 1.f)) return __fdiv_rn(a, b);
-  const float q = __fmul_rn(a, y);
-  const float r = __fmaf_rn(-q, b, a);
-  return __fmaf_rn(r, y, q);
-}
-
-// Pixel coordinate the reference ends up sampling at, along one axis of size sm1 + 1:
-//   corr.py:84-86       centroid / 2**i + delta          (division by a power of two is exact)
-//   utils.py:66         g = 2 * x / (W - 1) - 1
-//   grid_sampler_unnormalize, align_corners=True:  ((g + 1) / 2) * (W - 1)
-// every operation rounded separately in fp32 (no FMA contraction); the one real division uses the
-// hoisted reciprocal of (size - 1): same value, a third of the instructions.
-__device__ __forceinline__ float sample_coord_fast(float c, int lvl, int off, float sm1, float inv_sm1, int mode) {
-  const float x = __fadd_rn(__fmul_rn(c, 1.0f / (float)(1 << lvl)), (float)off);
-  if (mode == B200CORR_LOOKUP_DIRECT) return x;
-  const float g = __fsub_rn(div_by(__fmul_rn(2.0f, x), sm1, inv_sm1), 1.0f);
-  return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), sm1);   // x / 2 == x * 0.5 exactly
-}
-
-// one tap of one axis: position relative to the window origin `org` (or -1) and fraction
-template <int R>
-__device__ __forceinline__ void one_tap(float c, int lvl, int t, float sm1, float inv_sm1, int mode, int org,
-                                        int &rel, float &frac) {
-  constexpr int WS = 2 * R + 4;
-  const float x = sample_coord_fast(c, lvl, t - R, sm1, inv_sm1, mode);
-  const float fx = floorf(x);
-  if (fabsf(fx) < 1e8f) {
-    rel = (int)fx - org;
-    frac = x - fx;
-    // the round trip moves x by a few ulp at most: rel is within [0, WS-2]; clamp defensively
-    if (rel < 0 || rel > WS - 2) { rel = -1; frac = 0.f; }
-  } else {
-    rel = 0; frac = x - x;  // NaN propagates like in the reference
-  }
-}
-
-// Window origin floor(c / 2^l) - R - 1 from the un-rounded centre, and the window rows/columns
-// [lo, hi] the taps can touch: the coordinate arithmetic (fp32 add, and in grid_sample mode the
-// normalise / un-normalise round trip) moves a sample position by < 1e-3 pixel for |c| < 1024, so
-// unless the centre sits within 1/64 pixel of an integer, tap t lands exactly on window position
-// t + 1 and the outermost row/column on either side is never read.
-template <int R>
-__device__ __forceinline__ int window_origin(float c, int lvl, int &lo, int &hi) {
-  const float cl = c * (1.0f / (float)(1 << lvl));
-  float fo = floorf(cl);
-  const float f = cl - fo;
-  const bool interior = fabsf(cl) < 1024.f && f > 0.015625f && f < 0.984375f;
-  lo = interior ? 1 : 0;
-  hi = interior ? 2 * R + 2 : 2 * R + 3;
-  if (!(fabsf(fo) < 1e8f)) fo = -1e8f;  // non-finite / absurd coordinates: everything out of range
-  return (int)fo - R - 1;
-}
-
-constexpr int kCols = 16;  // staged columns per window row: (ox & 3) + 2r + 4 <= 15 for r <= 4
-enum { PATH_SCALAR = 0, PATH_VEC4 = 1, PATH_SECTOR = 2 };
-
-struct StageArgs {
-  const float *slice;  // this lane's H_l x W_l slice
-  int oy, ox, LH, LW;  // window origin, level extent
-  int ylo, yhi;        // window rows the taps touch
-  int clo, chi;        // staged columns the taps touch
-  bool q_ok;
-  bool blocked;        // PATH_SECTOR only: the slice is a grid of 8x8 tiles (64 consecutive floats each)
-  int tiles_w;         // tiles per row of a blocked slice
-};
-
-// Stage window rows r0 .. r0+NR-1 (those below WS) of this lane's query: win[row][column][lane].
-// Staged column 0 is level column (ox & ~3) for the vector flavours, ox itself for the scalar one.
-// Only the rows and the 32-byte sectors the taps touch are fetched; everything outside the slice is
-// staged as zero (= grid_sample's zero padding).
-// Two phases so that the tap tables (ALU work that needs only the coordinates) run while the loads are in flight:
-// stage_load issues every global load of this warp's rows into registers, stage_store parks them in the tile.
-template <int PATH, int NR, int WS>
-__device__ __forceinline__ void stage_load(const StageArgs &a, int r0, float (&v)[NR][24]) {
-  constexpr int NL = PATH == PATH_SECTOR ? 24 : PATH == PATH_VEC4 ? 16 : 12;   // loaded
-  // first loaded column: sector aligned / 16-byte aligned / exact
-  const int c0 = PATH == PATH_SECTOR ? (a.ox & ~7) : PATH == PATH_VEC4 ? (a.ox & ~3) : a.ox;
-  const bool hi4 = (a.ox & 4) != 0;  // PATH_SECTOR: staged column 0 is loaded column 4
-  // columns the taps touch, in loaded-column units
-  const int llo = PATH == PATH_SECTOR && hi4 ? a.clo + 4 : a.clo, lhi = PATH == PATH_SECTOR && hi4 ? a.chi + 4 : a.chi;
-#pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const int wr = r0 + r, y = a.oy + wr;
-    const bool row_ok = a.q_ok && wr >= a.ylo && wr <= a.yhi && y >= 0 && y < a.LH;
-    const float *src = a.slice + (size_t)(row_ok ? y : 0) * a.LW + c0;
-#pragma unroll
-    for (int k = 0; k < NL; ++k) v[r][k] = 0.f;
-    if (PATH == PATH_SECTOR) {
-#pragma unroll
-      for (int g = 0; g < 3; ++g) {   // one 32-byte sector per load
-        const int x = c0 + 8 * g;
-        if (row_ok && x >= 0 && x < a.LW && lhi >= 8 * g && llo < 8 * g + 8) {
-          const float *sp = a.blocked ? a.slice + ((size_t)((y >> 3) * a.tiles_w + (x >> 3)) * 64 + (y & 7) * 8)
-                                      : src + 8 * g;
-          ldg256(sp, *reinterpret_cast<float(*)[8]>(&v[r][8 * g]));
-        }
-      }
-    } else if (PATH == PATH_VEC4) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int x = c0 + 4 * g;
-        if (row_ok && x >= 0 && x < a.LW && lhi >= 4 * g && llo < 4 * g + 4)
-          ldg128(src + 4 * g, *reinterpret_cast<float(*)[4]>(&v[r][4 * g]));
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < NL; ++k)
-        if (row_ok && c0 + k >= 0 && c0 + k < a.LW) v[r][k] = __ldg(src + k);
-    }
-  }
-}
-
-template <int PATH, int NR, int WS>
-__device__ __forceinline__ void stage_store(float *win, int lane, const StageArgs &a, int r0, const float (&v)[NR][24]) {
-  constexpr int NC = PATH == PATH_SCALAR ? 12 : 16;                            // staged
-  const bool hi4 = (a.ox & 4) != 0;
-#pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    float *dst = win + ((r0 + r) * kCols) * 32 + lane;
-    if (r0 + r < WS) {
-#pragma unroll
-      for (int k = 0; k < NC; ++k) dst[k * 32] = (PATH == PATH_SECTOR) ? (hi4 ? v[r][k + 4] : v[r][k]) : v[r][k];
-    }
-  }
-}
+using namespace b200lookup;
 
 // CTA = 4 warps x the same 32 queries of one level; lane = query everywhere.
 //   warp w stages window rows w*RPW .. and computes every 4th tap table entry   -> one barrier
@@ -622,29 +450,6 @@ pool_bwd_vec4_kernel(float *__restrict__ fine, const float *__restrict__ coarse,
     v.x += c0; v.y += c0; v.z += c1; v.w += c1;
     *f = v;
   }
-}
-
-int fill_params(LookupParams &p, const float *const *lv, float *const *glv, int num_levels, int B,
-                int H, int W, int radius, int mode, const char *who, int first_level = 0) {
-  B200_CHECK(num_levels >= 1 && num_levels <= kMaxLevels, "%s: num_levels must be in [1, %d]", who,
-             kMaxLevels);
-  B200_CHECK(radius >= 1 && radius <= 4, "%s: radius %d not instantiated (1..4)", who, radius);
-  B200_CHECK(mode == B200CORR_LOOKUP_GRIDSAMPLE || mode == B200CORR_LOOKUP_DIRECT, "%s: bad mode", who);
-  B200_CHECK(B >= 0 && H >= 1 && W >= 1, "%s: bad sizes", who);
-  B200_CHECK(first_level >= 0 && first_level + num_levels <= 16, "%s: bad first_level %d", who, first_level);
-  p.num_levels = num_levels; p.B = B; p.HW = H * W; p.radius = radius; p.mode = mode; p.first_level = first_level;
-  int h = H >> first_level, w = W >> first_level;
-  for (int l = 0; l < kMaxLevels; ++l) {
-    p.lvl[l] = nullptr; p.glvl[l] = nullptr; p.LH[l] = 0; p.LW[l] = 0; p.path[l] = 0; p.blocked[l] = 0; p.tiles_w[l] = 0; p.slice[l] = 0;
-    if (l < num_levels) {
-      p.LH[l] = h; p.LW[l] = w; p.slice[l] = (long long)h * w;
-      B200_CHECK(h >= 1 && w >= 1, "%s: pyramid level %d is empty (%dx%d input)", who, l, H, W);
-      if (lv) { B200_CHECK(lv[l], "%s: null level %d", who, l); p.lvl[l] = lv[l]; }
-      if (glv) { B200_CHECK(glv[l], "%s: null gradient level %d", who, l); p.glvl[l] = glv[l]; }
-      h /= 2; w /= 2;
-    }
-  }
-  return 0;
 }
 
 }  // namespace

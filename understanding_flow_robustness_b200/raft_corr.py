@@ -139,6 +139,56 @@ def lookup_forward(levels, coords, radius, H, W, mode="grid_sample", first_level
     return out
 
 
+_CONVC1_CACHE = {}
+
+
+def prepare_convc1(weight, num_levels, radius):
+    """Prepared (TF32-rounded, per-level, zero-padded) copy of a convc1 weight `(n_out, L*(2r+1)^2[, 1, 1])` for
+    `lookup_convc1_forward`; cached per (storage, version), i.e. recomputed after an optimiser step."""
+    w = weight.detach()
+    n_out = w.shape[0]
+    w2 = w.reshape(n_out, -1).contiguous().float()
+    if w2.shape[1] != num_levels * (2 * radius + 1) ** 2:
+        raise RuntimeError(f"prepare_convc1: weight has {w2.shape[1]} input channels, expected "
+                           f"{num_levels} * {(2 * radius + 1) ** 2}")
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), num_levels, radius, weight.device)
+    hit = _CONVC1_CACHE.get(key)
+    if hit is not None:
+        return hit
+    _require_cuda_f32("prepare_convc1", w2)
+    L = _lib.lib()
+    nbytes = L.b200corr_lookup_convc1_weight_bytes(num_levels, radius, n_out)
+    wp = torch.empty(nbytes // 4, dtype=torch.float32, device=w2.device)
+    with torch.cuda.device(w2.device):
+        code = L.b200corr_lookup_convc1_prepare(_lib.ptr(w2), _lib.ptr(wp), num_levels, radius, n_out,
+                                                _lib.current_stream(w2.device))
+    _lib.check(code, "b200corr_lookup_convc1_prepare")
+    if len(_CONVC1_CACHE) > 8:
+        _CONVC1_CACHE.clear()
+    _CONVC1_CACHE[key] = wp
+    return wp
+
+
+def lookup_convc1_forward(levels, coords, wprep, bias, n_out, radius, H, W, mode="grid_sample", blocked_levels=0,
+                          relu=True):
+    """act(convc1(lookup(levels, coords))) without materialising the lookup: (B, n_out, H, W).
+    models/raft/raft.py:189 + models/raft/update.py:104,111 as one kernel (include/b200corr.h)."""
+    coords = coords.contiguous()
+    _require_cuda_f32("lookup_convc1_forward", coords, wprep, *levels)
+    if bias is not None:
+        bias = bias.detach().contiguous().float()
+        _require_cuda_f32("lookup_convc1_forward", coords, bias)
+    B = coords.shape[0]
+    out = torch.empty((B, n_out, H, W), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        code = _lib.lib().b200corr_lookup_convc1_forward(
+            _lib.ptr_array(levels), len(levels), blocked_levels, _lib.ptr(coords), _lib.ptr(wprep),
+            _lib.ptr(bias) if bias is not None else None, _lib.ptr(out), B, H, W, radius, LOOKUP_MODES[mode], n_out,
+            1 if relu else 0, _lib.current_stream(coords.device))
+    _lib.check(code, "b200corr_lookup_convc1_forward")
+    return out
+
+
 def allpairs_volume_rect(fmap1, fmap2, precision="tf32x3"):
     """(B*H1*W1, 1, H2, W2) volume of f1 (queries) against a key map of another size (AlternateCorrBlock's
     pooled f2): vol[b,p1,y,x] = f1[b,:,p1] . f2[b,:,y,x] / sqrt(C).  Tensor-core precisions, W2 % 4 == 0."""
@@ -417,6 +467,24 @@ class CorrBlock:
             return _LookupFunction.apply(self._handle, coords, self)
         return lookup_forward(self._levels, coords, self.radius, self.H, self.W, self.lookup_mode,
                               blocked_levels=self._blocked)
+
+    def lookup_convc1(self, coords, weight, bias=None, relu=True):
+        """`F.relu(convc1(self(coords)))` (models/raft/update.py:104,111 on top of raft.py:189) as ONE kernel: the
+        (B, L*(2r+1)^2, H, W) lookup result stays in shared memory / TMEM.  Inference path (no autograd through
+        the fused kernel): under grad mode with differentiable features or weights the unfused chain runs instead,
+        so gradients are always those of the reference."""
+        coords = coords.detach().float()
+        n_out = weight.shape[0]
+        needs_grad = torch.is_grad_enabled() and (self._handle is not None or weight.requires_grad or
+                                                  (bias is not None and bias.requires_grad))
+        fused_ok = (not self.compute_spatial and not needs_grad and n_out % 32 == 0 and n_out <= 256 and
+                    self.B > 0 and 1 <= self.radius <= 4)
+        if not fused_ok:
+            out = F.conv2d(self(coords), weight.reshape(n_out, -1, 1, 1), bias)
+            return F.relu(out) if relu else out
+        wp = prepare_convc1(weight, self.num_levels, self.radius)
+        return lookup_convc1_forward(self._levels, coords, wp, bias, n_out, self.radius, self.H, self.W,
+                                     self.lookup_mode, self._blocked, relu)
 
     @staticmethod
     def corr(fmap1, fmap2, precision="tf32x3"):
