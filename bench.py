@@ -1011,6 +1011,23 @@ def raft_bench(dev):
         lbwd_fn, _ = graphed(lambda: raft_corr.lookup_backward(glv, coords[0], gout, c["radius"], H, W))
         lookup_bwd_ms = timed(lbwd_fn, 10)
         del glv, gout
+        # the lookup fused with the motion encoder's convc1 (1x1, 324 -> 256) + bias + ReLU
+        # (update.py:104,111) against lookup -> cuDNN 1x1 convolution -> ReLU (torch's default allow_tf32)
+        conv = torch.nn.Conv2d(c["levels"] * (2 * c["radius"] + 1) ** 2, 256, 1).to(dev)
+        import torch.nn.functional as F
+        fused_fn, how_fused = graphed(lambda: blk[0].lookup_convc1(coords[0], conv.weight, conv.bias))
+        fused_ms = timed(fused_fn, 10)
+        unf_fn, _ = graphed(lambda: F.relu(conv(blk[0](coords[0]))))
+        unf_ms = timed(unf_fn, 10)
+        look1_fn, _ = graphed(lambda: blk[0](coords[0]))
+        look1_ms = timed(look1_fn, 10)
+        fuse_row = {"fused_ms": fused_ms, "unfused_ms": unf_ms, "lookup_alone_ms": look1_ms, "speedup": unf_ms / fused_ms,
+                    "timed_loop": how_fused,
+                    "bytes_not_moved_per_iter": 2 * B * 324 * H * W * 4,
+                    "what": "CorrBlock.lookup_convc1 (one tcgen05 kernel: gather -> TF32 operand tile -> MMA over the 4 "
+                            "levels -> bias + ReLU) vs lookup kernel + cuDNN 1x1 conv (TF32 allowed) + ReLU; the "
+                            "(B,324,H,W) lookup result is neither written nor read back"}
+        del conv
         blk[0] = None
         x3_fn, _ = graphed(lambda: raft_corr.allpairs_pyramid(f1, f2, c["levels"], "tf32x3"))
         build_x3_ms = timed(x3_fn, 3)
@@ -1033,6 +1050,7 @@ def raft_bench(dev):
                               "rowmajor_ms_per_iter": (build_rm_ms + c["iters"] * look_rm_ms) / c["iters"]},
             "alt_corr_ms_per_iter": alt_ms,
             "alt_corr": alt_rows, "lookup_backward_ms": lookup_bwd_ms, "build_tf32x3_ms": build_x3_ms,
+            "lookup_convc1": fuse_row,
             "config": f"B={B}, {C}x{H}x{W}, {c['levels']} levels, radius {c['radius']}, {c['iters']} lookups, TF32 volume",
             "timed_loop": {"build": how_build, "lookups": how_look},
             "roofline_build": {"bound": "hbm", "achieved": vol_bytes / (build_ms * 1e-3) / 1e9, "peak": hbm,

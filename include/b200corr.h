@@ -285,13 +285,6 @@ int b200corr_patch_compose_backward(const float *img1, const float *img2, const 
  * *tflops (used by bench.py for the FP32-pipe roofline denominator). */
 int b200corr_measure_fp32_peak(int iters, float *tflops, void *stream);
 
-/* Window-gather ceiling of the memory system (the RAFT lookup's roofline; scripts/probes/gather_probe.cu):
- * `nslices` contiguous slices of slice_bytes in buf (caller-provided, e.g. pyramid level 0), one
- * 10-row x 64-byte window per slice at pitch_bytes per row, nothing else.  Returns 1e9 window rows
- * per second in *grows_per_s. */
-int b200corr_measure_gather_peak(const float *buf, long long nslices, int slice_bytes, int pitch_bytes,
-                                 float *grows_per_s, void *stream);
-
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t b200corr_launch_count(void);
 

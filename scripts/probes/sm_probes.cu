@@ -3,7 +3,8 @@
 //     (how many wavefronts a multicast 128-bit load costs);
 //   * FP32 FFMA rate of the register-blocked Toeplitz update the sampler forward issues
 //     (acc[t][k] += a[t] * v[t + 2k], 8 x 21 accumulators per thread).
-// Diagnostics only; nothing on the data path calls these.
+// Diagnostics only, built into their own library (scripts/probe_sm.py: libb200probes.so = this file +
+// csrc/common.cu); the product library libb200corr.so does not contain them.
 #include "common.cuh"
 
 namespace {

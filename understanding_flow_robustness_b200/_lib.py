@@ -60,11 +60,7 @@ PROTOTYPES = {
     "b200corr_patch_compose_backward": (c_int, [c_void_p] * 9 + [c_size_t] + [c_int] * 4 + [ctypes.c_longlong] * 4
                                         + [c_void_p]),
     "b200corr_measure_fp32_peak": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p]),
-    "b200corr_measure_gather_peak": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, ctypes.POINTER(c_float), c_void_p]),
     "b200corr_launch_count": (ctypes.c_uint64, []),
-    "b200corr_probe_lds": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float), c_void_p]),
-    "b200corr_probe_ffma_toeplitz": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p]),
-    "b200corr_probe_ffma2_peak": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p]),
 }
 
 

@@ -8,6 +8,8 @@ Same argument order and meaning; the checks the reference does with TORCH_CHECK
 too, plus shape/dtype validation the reference leaves out.  CUDA tensors only: the reference's CPU
 branch (:76-86) has no counterpart in this package.
 """
+import collections
+
 import torch
 
 from . import _lib
@@ -62,26 +64,39 @@ def forward(input1, input2, kH, kW, patchH, patchW, padH, padW, dilationH, dilat
     return out
 
 
-_PLANS = {}
+_PLANS = collections.OrderedDict()      # (device, shape, hyper, dtype) -> device plan, least recently used first
+_PLAN_CAPACITY = 64
 
 
 def _backward_plan(device, B, C, H, W, hyper, dt):
-    """Device copy of the library's backward schedule, built once per (device, problem shape)."""
+    """Device copy of the library's backward schedule, built once per (device, problem shape).
+
+    The upload goes through a pinned buffer and is complete before this returns (the plan is then read by
+    kernels on whatever stream a later call uses); eviction is least-recently-used and a plan is only dropped
+    after the device has finished everything queued so far.  A cold cache inside a CUDA graph capture is an
+    error: warm the shape up once before capturing."""
     key = (device, B, C, H, W, hyper, dt)
     plan = _PLANS.get(key)
-    if plan is None:
-        L = _lib.lib()
-        nbytes = L.b200corr_sampler_backward_workspace_bytes(B, C, H, W, *hyper, dt)
-        if nbytes == 0:
-            plan = False
-        else:
-            host = torch.empty(nbytes // 4, dtype=torch.int32)
-            _lib.check(L.b200corr_sampler_backward_plan(B, C, H, W, *hyper, dt, host.data_ptr(), nbytes),
-                       "b200corr_sampler_backward_plan")
-            plan = host.to(device)
-        if len(_PLANS) > 64:
-            _PLANS.clear()
-        _PLANS[key] = plan
+    if plan is not None:
+        _PLANS.move_to_end(key)
+        return plan
+    L = _lib.lib()
+    nbytes = L.b200corr_sampler_backward_workspace_bytes(B, C, H, W, *hyper, dt)
+    if nbytes == 0:
+        plan = False
+    else:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("correlation backward: first call for this shape inside a CUDA graph capture; run the "
+                               "backward once before capturing (the schedule is uploaded on first use)")
+        host = torch.empty(nbytes // 4, dtype=torch.int32).pin_memory()
+        _lib.check(L.b200corr_sampler_backward_plan(B, C, H, W, *hyper, dt, host.data_ptr(), nbytes),
+                   "b200corr_sampler_backward_plan")
+        plan = host.to(device, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+    if len(_PLANS) >= _PLAN_CAPACITY:
+        torch.cuda.synchronize(device)              # nothing in flight still reads the evicted plan
+        _PLANS.popitem(last=False)
+    _PLANS[key] = plan
     return plan
 
 

@@ -72,7 +72,8 @@ resample2d_fwd_kernel(const float *__restrict__ in, const float *__restrict__ fl
     val += (float)((alpha) * (beta) * p[(long long)c.yB * W + c.xR]);
     out[i] = val;
   } else {
-    const int xN = max(min((int)floorf(xf + 0.5f), W - 1), 0), yN = max(min((int)floorf(yf + 0.5f), H - 1), 0);
+    // floor(x + 0.5) in double, as resample2d_kernel.cu:52-53 computes it (an fp32 add can round up to the next integer)
+    const int xN = max(min((int)floor((double)xf + 0.5), W - 1), 0), yN = max(min((int)floor((double)yf + 0.5), H - 1), 0);
     out[i] = p[(long long)yN * W + xN];
   }
 }
