@@ -903,6 +903,8 @@ def merge_bench(dev):
 
 def raft_bench(dev):
     """RAFT CorrBlock, BASELINE config 3: ms/iter := (pyramid build + 12 lookups) / 12, HBM roofline."""
+    import math
+
     import torch
 
     from understanding_flow_robustness_b200 import AlternateCorrBlock, CorrBlock, coords_grid
@@ -1010,6 +1012,8 @@ def raft_bench(dev):
         gout = torch.randn(B, c["levels"] * (2 * c["radius"] + 1) ** 2, H, W, device=dev)
         lbwd_fn, _ = graphed(lambda: raft_corr.lookup_backward(glv, coords[0], gout, c["radius"], H, W))
         lookup_bwd_ms = timed(lbwd_fn, 10)
+        vbwd_fn, _ = graphed(lambda: raft_corr.volume_backward(glv, f1, f2, 1.0 / math.sqrt(C), "tf32"))
+        vol_bwd_ms = timed(vbwd_fn, 5)
         del glv, gout
         # the lookup fused with the motion encoder's convc1 (1x1, 324 -> 256) + bias + ReLU
         # (update.py:104,111) against lookup -> cuDNN 1x1 convolution -> ReLU (torch's default allow_tf32)
@@ -1051,6 +1055,8 @@ def raft_bench(dev):
             "alt_corr_ms_per_iter": alt_ms,
             "alt_corr": alt_rows, "lookup_backward_ms": lookup_bwd_ms, "build_tf32x3_ms": build_x3_ms,
             "lookup_convc1": fuse_row,
+            "volume_backward_ms": vol_bwd_ms,
+            "corrblock_backward_12_lookups_ms": 12 * lookup_bwd_ms + vol_bwd_ms,
             "config": f"B={B}, {C}x{H}x{W}, {c['levels']} levels, radius {c['radius']}, {c['iters']} lookups, TF32 volume",
             "timed_loop": {"build": how_build, "lookups": how_look},
             "roofline_build": {"bound": "hbm", "achieved": vol_bytes / (build_ms * 1e-3) / 1e9, "peak": hbm,

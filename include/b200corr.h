@@ -241,6 +241,19 @@ int b200corr_lookup_backward(float *const *h_grad_levels, int num_levels, const 
 int b200corr_pyramid_backward(float *const *h_grad_levels, int num_levels, int B, int H, int W,
                               void *stream);
 
+/* Backward of the volume + pyramid w.r.t. the feature maps (what autograd derives for corr.py:55-64,98-106):
+ * h_grad_levels[l] = dL/d vol_l, (B*H*W, 1, H>>l, W>>l) row-major, as b200corr_lookup_backward leaves them
+ * (NOT folded: do not call b200corr_pyramid_backward first).  Writes (overwrites)
+ *   grad_fmap1 = scale * sum_l G_l . pool_l(fmap2)^T      grad_fmap2 = scale * sum_l unpool_l(G_l^T . fmap1) / 4^l
+ * which equals scale * fold(G) . F2^T and scale * fold(G)^T . F1 because average pooling commutes with the
+ * contraction.  precision B200CORR_PREC_FP32: exact fp32 (CUDA cores); otherwise TF32 tensor cores (operands
+ * truncated to TF32, fp32 accumulation), falling back to the exact kernel for shapes TMA cannot express.
+ * workspace: b200corr_volume_backward_workspace_bytes (pooled copies of fmap2 and their gradients). */
+size_t b200corr_volume_backward_workspace_bytes(int num_levels, int B, int C, int H, int W);
+int b200corr_volume_backward(const float *const *h_grad_levels, int num_levels, const float *fmap1,
+                             const float *fmap2, float *grad_fmap1, float *grad_fmap2, int B, int C, int H, int W,
+                             float scale, int precision, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------- alt_cuda_corr */
 
 /* fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C] (NHWC), coords [B,N,H1,W1,2] -> corr [B,N,(2r+1)^2,H1,W1],

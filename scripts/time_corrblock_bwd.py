@@ -1,5 +1,6 @@
 """Breakdown of the CorrBlock backward (B=4, 256x48x160, 12 lookups): gradient-pyramid zero fill, 12 lookup
-backward launches, pyramid fold, the two gradient GEMMs (GPU box)."""
+backward launches, then round 2's volume backward (csrc/raft_volume_bwd.cu: feature pooling + two tcgen05 GEMMs
+over the unfolded pyramid + unpool) next to what it replaced (pyramid fold + two cuBLAS GEMMs) (GPU box)."""
 import json
 import math
 import os
@@ -34,6 +35,7 @@ glv = [torch.zeros(B * H * W, 1, h, w, device="cuda") for h, w in shapes]
 res = {"zero_fill_ms": t(lambda: [v.zero_() for v in glv]),
        "lookup_bwd_x12_ms": t(lambda: [raft_corr.lookup_backward(glv, c, g, 4, H, W) for c in cs]),
        "pyramid_fold_ms": t(lambda: raft_corr.pyramid_backward(glv, B, H, W))}
+res["volume_backward_tf32_ms"] = t(lambda: raft_corr.volume_backward(glv, f1, f2, 1.0 / 16.0, "tf32"))
 gvol = glv[0].view(B, H * W, H * W)
 for tf32 in (True, False):
     torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -43,7 +45,7 @@ f1g, f2g = f1.clone().requires_grad_(), f2.clone().requires_grad_()
 
 
 def whole():
-    blk = CorrBlock(f1g, f2g, 4, 4)
+    blk = CorrBlock(f1g, f2g, 4, 4, precision="tf32")
     loss = sum(blk(c).sum() for c in cs)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

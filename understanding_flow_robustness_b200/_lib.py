@@ -53,6 +53,9 @@ PROTOTYPES = {
     "b200corr_lookup_backward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_int,
                                          c_int, c_int, c_int, c_void_p]),
     "b200corr_pyramid_backward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),
+    "b200corr_volume_backward_workspace_bytes": (c_size_t, [c_int] * 5),
+    "b200corr_volume_backward": (c_int, [ctypes.POINTER(c_void_p), c_int] + [c_void_p] * 4 + [c_int] * 4
+                                 + [c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "b200corr_altcorr_forward": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
     "b200corr_altcorr_backward": (c_int, [c_void_p] * 7 + [c_int] * 8 + [c_void_p]),
     "b200corr_patch_compose_forward": (c_int, [c_void_p] * 7 + [c_int] * 4 + [ctypes.c_longlong] * 4 + [c_void_p]),

@@ -231,18 +231,25 @@ def pyramid_backward(grad_levels, B, H, W):
     _lib.check(code, "b200corr_pyramid_backward")
 
 
-def volume_backward(gvol, fmap1, fmap2, scale, precision):
-    """dF1 = scale * gvol . F2^T, dF2 = scale * gvol^T . F1 for gvol (B*HW, 1, H, W): what autograd derives for
-    `torch.matmul(fmap1^T, fmap2)` (models/raft/corr.py:104) -- in the precision the volume was built with."""
+def volume_backward(grad_levels, fmap1, fmap2, scale, precision):
+    """dF1 = scale * fold(G) . F2^T, dF2 = scale * fold(G)^T . F1 from the UNFOLDED per-level gradients: what autograd
+    derives for `torch.matmul(fmap1^T, fmap2)` + 3 x `avg_pool2d` (models/raft/corr.py:55-64,104).  The fold is
+    moved onto the feature maps (average pooling commutes with the contraction), the two products run on the
+    tensor cores in TF32 (precision "tf32" / "tf32x3") or exactly on the CUDA cores ("fp32")."""
+    fmap1 = fmap1.contiguous()
+    fmap2 = fmap2.contiguous()
+    _require_cuda_f32("volume_backward", fmap1, fmap2, *grad_levels)
     B, C, H, W = fmap1.shape
-    g = gvol.view(B, H * W, H * W)
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = precision == "tf32"
-    try:
-        g1 = torch.bmm(fmap2.reshape(B, C, H * W), g.transpose(1, 2)).mul_(scale).view_as(fmap1)
-        g2 = torch.bmm(fmap1.reshape(B, C, H * W), g).mul_(scale).view_as(fmap2)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
+    L = _lib.lib()
+    g1 = torch.empty_like(fmap1)
+    g2 = torch.empty_like(fmap2)
+    nbytes = L.b200corr_volume_backward_workspace_bytes(len(grad_levels), B, C, H, W)
+    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=fmap1.device)
+    with torch.cuda.device(fmap1.device):
+        code = L.b200corr_volume_backward(_lib.ptr_array(grad_levels), len(grad_levels), _lib.ptr(fmap1), _lib.ptr(fmap2),
+                                          _lib.ptr(g1), _lib.ptr(g2), B, C, H, W, scale, PRECISIONS[precision],
+                                          _lib.ptr(ws), nbytes, _lib.current_stream(fmap1.device))
+    _lib.check(code, "b200corr_volume_backward")
     return g1, g2
 
 
@@ -323,11 +330,12 @@ class _GradState:
     autograd handle: the graph (handle -> grad_fn -> ctx) must not keep the 1.25 GB volume alive, nor form a
     cycle with the block (the reference's pyramid is freed by refcount when `corr_fn` goes out of scope)."""
 
-    __slots__ = ("B", "H", "W", "num_levels", "radius", "lookup_mode", "precision", "grad_levels")
+    __slots__ = ("B", "H", "W", "num_levels", "radius", "lookup_mode", "precision", "backward_precision", "grad_levels")
 
-    def __init__(self, B, H, W, num_levels, radius, lookup_mode, precision):
+    def __init__(self, B, H, W, num_levels, radius, lookup_mode, precision, backward_precision):
         self.B, self.H, self.W, self.num_levels = B, H, W, num_levels
         self.radius, self.lookup_mode, self.precision = radius, lookup_mode, precision
+        self.backward_precision = backward_precision
         self.grad_levels = None
 
 
@@ -352,8 +360,7 @@ class _VolumeFunction(torch.autograd.Function):
         st.grad_levels = None
         if gl is None:
             return torch.zeros_like(fmap1), torch.zeros_like(fmap2), None
-        pyramid_backward(gl, B, H, W)
-        g1, g2 = volume_backward(gl[0], fmap1, fmap2, 1.0 / math.sqrt(C), st.precision)
+        g1, g2 = volume_backward(gl, fmap1, fmap2, 1.0 / math.sqrt(C), st.backward_precision)
         return g1, g2, None
 
 
@@ -383,11 +390,15 @@ class CorrBlock:
     """models/raft/corr.py:26-106."""
 
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, compute_spatial=False, precision=None,
-                 lookup_mode="grid_sample", layout="auto"):
+                 lookup_mode="grid_sample", layout="auto", backward_precision=None):
         """precision: "tf32x3" (default: split-TF32 on the tensor cores, the accuracy of the reference's fp32
         matmul), "tf32" (one TF32 pass, half the build time, |err| <= 2^-10 * sum|f1 f2| / sqrt(C)) or "fp32"
         (CUDA cores).  None reads the environment variable B200CORR_VOLUME_PRECISION, so a caller that cannot
         pass arguments (the unmodified models/raft/raft.py:150-156) can still choose.
+        backward_precision: precision of the two gradient contractions dF = G . F: "tf32" (tensor cores, operands
+        truncated to TF32: relative 2^-10 per product, the default for the tensor-core forward precisions -- what
+        cuBLAS computes for the reference when TF32 is allowed) or "fp32" (exact, CUDA cores; the default for
+        precision="fp32").  B200CORR_VOLUME_BACKWARD_PRECISION overrides the default.
         layout: "auto" keeps the two fine levels in the blocked layout (8x8 tiles, include/b200corr.h) where the
         library supports the problem -- the lookups read them 1.4x faster; `corr_pyramid` / `get_corr_pyramid()`
         still hand out the reference's row-major tensors (converted on first use).  "rowmajor": as the reference."""
@@ -420,7 +431,13 @@ class CorrBlock:
                 self._levels.append(corr)
         else:
             self.B, self.C, self.H, self.W = fmap1.shape
-            self._state = _GradState(self.B, self.H, self.W, num_levels, radius, lookup_mode, precision)
+            if backward_precision is None:
+                backward_precision = os.environ.get("B200CORR_VOLUME_BACKWARD_PRECISION",
+                                                    "fp32" if precision == "fp32" else "tf32")
+            if backward_precision not in ("tf32", "fp32"):
+                raise ValueError("CorrBlock: backward_precision must be 'tf32' or 'fp32'")
+            self._state = _GradState(self.B, self.H, self.W, num_levels, radius, lookup_mode, precision,
+                                     backward_precision)
             needs_grad = torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad)
             if needs_grad:
                 self._handle = _VolumeFunction.apply(fmap1.contiguous(), fmap2.contiguous(), self)
