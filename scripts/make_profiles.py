@@ -41,14 +41,15 @@ def shares(sel, title, out):
 
 with open(os.path.join(P, f"{R}_bench_kernel_shares.txt"), "w") as f:
     shares(lambda k: "sampler_" in k, "shares of the sampler step (the timed region of bench.py) from the ncu launch list", f)
-    shares(lambda k: "allpairs_tc" in k or "lookup_fwd" in k or "prep_kmajor" in k,
+    shares(lambda k: "allpairs_tc" in k or "lookup_fwd" in k or "prep_kmajor" in k or "lookup_convc1" in k or "volgrad" in k,
            "shares of the RAFT build + lookup from the ncu launch list", f)
     shares(lambda k: True, "all kernels of the bench command (first 600 launches)", f)
 
 # ---- full captures
 summ = os.path.join(ROOT, "scripts", "ncu_summary.py")
 for name, what in (("sampler_full", "sampler"), ("raft_full", "raft: all-pairs + lookup forward"),
-                   ("raft_aux_full", "raft: lookup backward + alt_cuda_corr forward"),
+                   ("raft_aux_full", "raft: lookup backward, volume backward (tcgen05 GEMMs), alt_cuda_corr forward / backward"),
+                   ("lookup_convc1_full", "lookup fused with the motion encoder's 1x1 convolution (tcgen05)"),
                    ("merge_full", "fused FlowNetC merge block: forward kernel (1/C + LeakyReLU epilogue, concat slice) + backward pre-pass")):
     rep = os.path.join(G, f"{R}_{name}.ncu-rep")
     if not os.path.exists(rep):
@@ -81,7 +82,8 @@ if os.path.exists(rep):
     tr["source"] = f"profiles/{R}_sampler_full_summary.txt (ncu --set full, B=8, 256x48x160)"
     json.dump(tr, open(os.path.join(P, "sampler_traffic.json"), "w"), indent=1)
 
-for f in (f"{R}_bench_line.json", f"{R}_vs_reference_cuda.json"):
+for f in (f"{R}_bench_line.json", f"{R}_vs_reference_cuda.json", f"{R}_sweep_cfg5.json", f"{R}_attack_timeline_g1.json",
+          f"{R}_attack_timeline_g8.json", f"{R}_bench_line_g2.json", f"{R}_bench_line_g8.json"):
     if os.path.exists(os.path.join(G, f)):
         shutil.copy(os.path.join(G, f), os.path.join(P, f))
 print(sorted(os.listdir(P)))

@@ -12,9 +12,11 @@ ncu --set full --clock-control none --import-source on -k regex:sampler_ -s 3 -c
     python scripts/run_sampler_once.py 8 2 > $O/ncu_sampler.log 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:allpairs_tc|lookup_fwd" -s 3 -c 2 -f -o $O/${R}_raft_full \
     python scripts/run_raft_once.py 4 2 > $O/ncu_raft.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:lookup_bwd|altcorr_fwd" -s 2 -c 2 -f -o $O/${R}_raft_aux_full \
+ncu --set full --clock-control none --import-source on -k "regex:lookup_bwd|altcorr_fwd|altcorr_bwd|volgrad_tc" -s 2 -c 8 -f -o $O/${R}_raft_aux_full \
     python scripts/run_raft_aux_once.py > $O/ncu_raft_aux.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:lookup_convc1_kernel" -s 1 -c 1 -f -o $O/${R}_lookup_convc1_full \
+    python scripts/run_lookup_convc1_once.py > $O/ncu_lc1.log 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:merge_grad|sampler_fwd" -s 2 -c 2 -f -o $O/${R}_merge_full \
     python scripts/run_merge_once.py > $O/ncu_merge.log 2>&1
-python scripts/ref_cuda_compare.py > $O/ref_compare.log 2>&1; tail -3 $O/ref_compare.log
+python scripts/sweep_cfg5.py > $O/sweep_cfg5.log 2>&1; tail -2 $O/sweep_cfg5.log
 ls -la $O | tail -12

@@ -1,4 +1,4 @@
-"""Runs the RAFT lookup backward and the alt_cuda_corr forward a few times (ncu target)."""
+"""Runs the RAFT lookup backward, the volume backward and the alt_cuda_corr forward / backward a few times (ncu target)."""
 import os
 import sys
 
@@ -18,5 +18,9 @@ with torch.no_grad():
     for _ in range(3):
         raft_corr.lookup_backward(glv, c, g, 4, 48, 160, "grid_sample")
     alt = AlternateCorrBlock(f1, f2, 4, 4)(c)
+    raft_corr.volume_backward(glv, f1, f2, 1.0 / 16.0, "tf32")
+    f1n, f2n = f1.permute(0, 2, 3, 1).contiguous(), f2.permute(0, 2, 3, 1).contiguous()
+    cn = c.permute(0, 2, 3, 1).reshape(B, 1, 48, 160, 2).contiguous()
+    raft_corr.alt_cuda_corr.backward(f1n, f2n, cn, torch.randn(B, 1, 81, 48, 160, device="cuda"), 4)
 torch.cuda.synchronize()
 print("ok", float(glv[0].abs().max()), float(alt[0, 40, 5, 5]))

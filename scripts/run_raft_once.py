@@ -14,7 +14,7 @@ f2 = torch.randn(B, 256, 48, 160, device="cuda")
 c = coords_grid(B, 48, 160, "cuda") + 3.0 * torch.randn(B, 2, 48, 160, device="cuda")
 with torch.no_grad():
     for _ in range(reps):
-        blk = CorrBlock(f1, f2, 4, 4)
+        blk = CorrBlock(f1, f2, 4, 4, precision="tf32")
         o = blk(c)
         o2 = blk(c + 1.0)
     alt = AlternateCorrBlock(f1, f2, 4, 4)(c)
