@@ -1019,18 +1019,23 @@ def raft_bench(dev):
         # (update.py:104,111) against lookup -> cuDNN 1x1 convolution -> ReLU (torch's default allow_tf32)
         conv = torch.nn.Conv2d(c["levels"] * (2 * c["radius"] + 1) ** 2, 256, 1).to(dev)
         import torch.nn.functional as F
-        fused_fn, how_fused = graphed(lambda: blk[0].lookup_convc1(coords[0], conv.weight, conv.bias))
+        fused_fn, how_fused = graphed(lambda: blk[0].lookup_convc1(coords[0], conv.weight, conv.bias, impl="fused"))
         fused_ms = timed(fused_fn, 10)
+        pipe_fn, _ = graphed(lambda: blk[0].lookup_convc1(coords[0], conv.weight, conv.bias, impl="pipelined"))
+        pipe_ms = timed(pipe_fn, 10)
         unf_fn, _ = graphed(lambda: F.relu(conv(blk[0](coords[0]))))
         unf_ms = timed(unf_fn, 10)
         look1_fn, _ = graphed(lambda: blk[0](coords[0]))
         look1_ms = timed(look1_fn, 10)
-        fuse_row = {"fused_ms": fused_ms, "unfused_ms": unf_ms, "lookup_alone_ms": look1_ms, "speedup": unf_ms / fused_ms,
+        fuse_row = {"pipelined_ms": pipe_ms, "fused_ms": fused_ms, "unfused_ms": unf_ms, "lookup_alone_ms": look1_ms,
+                    "speedup_pipelined": unf_ms / pipe_ms, "speedup_fused": unf_ms / fused_ms,
                     "timed_loop": how_fused,
                     "bytes_not_moved_per_iter": 2 * B * 324 * H * W * 4,
-                    "what": "CorrBlock.lookup_convc1 (one tcgen05 kernel: gather -> TF32 operand tile -> MMA over the 4 "
-                            "levels -> bias + ReLU) vs lookup kernel + cuDNN 1x1 conv (TF32 allowed) + ReLU; the "
-                            "(B,324,H,W) lookup result is neither written nor read back"}
+                    "what": "CorrBlock.lookup_convc1 vs lookup kernel + cuDNN 1x1 conv (TF32 allowed) + ReLU.  fused: ONE "
+                            "tcgen05 kernel (gather -> TF32 operand tile -> MMA over the 4 levels -> bias + ReLU), the "
+                            "(B,324,H,W) lookup result is neither written nor read back; pipelined: lookup kernel + a "
+                            "tcgen05 1x1-conv kernel (MN-major operand straight from the lookup result, which is still in "
+                            "the L2), bias + ReLU in its epilogue"}
         del conv
         blk[0] = None
         x3_fn, _ = graphed(lambda: raft_corr.allpairs_pyramid(f1, f2, c["levels"], "tf32x3"))

@@ -229,6 +229,13 @@ int b200corr_lookup_convc1_forward(const float *const *h_levels, int num_levels,
                                    const float *coords, const float *wprep, const float *bias, float *out, int B,
                                    int H, int W, int radius, int mode, int n_out, int relu, void *stream);
 
+/* The same convolution as a stand-alone tensor-core kernel behind the plain lookup ("pipelined" variant of the row
+ * above; also usable for any 1x1 convolution): out[B, N, HW] = act(weight[N, K] . x[B, K, HW] + bias), TF32 tcgen05,
+ * x read as it lies (MN-major operand through TMA).  N <= 256, K % 4 == 0, HW % 4 == 0, 16-byte aligned operands;
+ * bias may be NULL; relu != 0 applies max(., 0). */
+int b200corr_conv1x1_forward(const float *x, const float *weight, const float *bias, float *out, int B, int K,
+                             int N, int HW, int relu, void *stream);
+
 /* Accumulates (+=) d(out)/d(level l) into h_grad_levels[l] (caller zero-initialises once per
  * CorrBlock; several lookups of the same block accumulate).  Coordinates get no gradient
  * (the reference detaches them, models/raft/raft.py:188). */

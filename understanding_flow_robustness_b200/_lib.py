@@ -50,6 +50,7 @@ PROTOTYPES = {
     "b200corr_lookup_convc1_prepare": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200corr_lookup_convc1_forward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p, c_void_p,
                                                c_void_p] + [c_int] * 7 + [c_void_p]),
+    "b200corr_conv1x1_forward": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "b200corr_lookup_backward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_int,
                                          c_int, c_int, c_int, c_void_p]),
     "b200corr_pyramid_backward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),

@@ -89,8 +89,10 @@ lookup_convc1_kernel(const __grid_constant__ CUtensorMap mapW, const fz::Params 
   uint64_t *w_full = bars, *w_empty = bars + NWST;
   uint64_t *a_full = bars + 2 * NWST, *a_empty = a_full + 1, *acc_full = a_full + 2, *acc_empty = a_full + 3;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 4);
+  __shared__ float bias_s[256];      // a global load per output channel in the epilogue costs a DRAM/L2 round trip each
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 256) bias_s[tid] = (p.bias && tid < p.n_out) ? p.bias[tid] : 0.f;
   const LookupParams &lp = p.lp;
   const int L = lp.num_levels;
 
@@ -290,7 +292,7 @@ lookup_convc1_kernel(const __grid_constant__ CUtensorMap mapW, const fz::Params 
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float x = v[i] + (p.bias ? __ldg(p.bias + c0 + i) : 0.f);
+            float x = v[i] + bias_s[c0 + i];
             if (p.relu) x = fmaxf(x, 0.f);
             if (ok) ob[(size_t)(c0 + i) * lp.HW] = x;
           }
@@ -304,6 +306,138 @@ lookup_convc1_kernel(const __grid_constant__ CUtensorMap mapW, const fz::Params 
   tc_fence_before();
   __syncthreads();
   if (warp == 17) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same convolution as a stand-alone tcgen05 GEMM behind the plain lookup kernel ("pipelined" variant):
+//     out[b, n, q] = act(sum_k W[n, k] * X[b, k, q] + bias[n])          X = the (B, K, H*W) lookup result
+// X is consumed where the lookup kernel left it: (B, K, HW) with q contiguous is an MN-major A operand
+// (M = 128 queries, TMA boxes of 32 queries x 32 channels, 128-byte swizzle with 32-byte atoms -- the one layout
+// the tensor core accepts for 32-bit MN-major operands), W (n_out, K) is a K-major B operand as it lies.  At B <= 4
+// the 39.8 MB of X are still in the 126 MB L2 when this kernel reads them.  TMEM holds two accumulators so that
+// the epilogue (bias, ReLU, coalesced stores: lane = query) of a tile overlaps the MMAs of the next.
+namespace cv {
+constexpr int BM = 128, BK = 32, NST = 4, THREADS = 192;
+constexpr int A_BYTES = BM * BK * 4, B_BYTES = 256 * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = 1024 + NST * STAGE_BYTES + 256;
+struct Params {
+  int B, K, N, NP, HW, tiles_per_b, total_tiles, kblocks, relu;   // NP = N rounded up to 16
+  const float *bias;
+  float *out;
+};
+__device__ __forceinline__ uint64_t desc_mnmajor_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+}  // namespace cv
+
+__global__ void __launch_bounds__(cv::THREADS, 1)
+conv1x1_mn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const cv::Params p) {
+  using namespace cv;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - raw);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sm + NST * STAGE_BYTES);
+  uint64_t *full_bar = bars, *empty_bar = bars + NST, *tfull = bars + 2 * NST, *tempty = tfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfull + 4);
+  __shared__ float bias_s[256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 256; i += THREADS) bias_s[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapW);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int b = t / p.tiles_per_b, m0 = (t - b * p.tiles_per_b) * BM;
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int st = it % NST;
+          mbar_wait(&empty_bar[st], ((it / NST) & 1) ^ 1);
+          uint8_t *a = sm + st * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[st], A_BYTES + (uint32_t)p.NP * BK * 4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_3d(a + j * 4096, &mapX, &full_bar[st], m0 + 32 * j, kb * BK, b);
+          tma_load_3d(a + A_BYTES, &mapW, &full_bar[st], kb * BK, 0, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(BM, p.NP) | (1u << 15);      // A MN-major
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int st = it % NST;
+          mbar_wait(&full_bar[st], (it / NST) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = base + st * STAGE_BYTES;
+          const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + A_BYTES);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_tf32(tmem_base + buf * 256, desc_mnmajor_sw128_32b(a_addr + k4 * 1024, 4096, 512), bdesc + 2 * k4, idesc,
+                      (kb | k4) != 0);
+          umma_commit(&empty_bar[st]);
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    const int wq = warp & 3;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int b = t / p.tiles_per_b, q = (t - b * p.tiles_per_b) * BM + wq * 32 + lane;
+      const bool ok = q < p.HW;
+      float *ob = p.out + ((size_t)b * p.N) * p.HW + q;
+      mbar_wait(&tfull[buf], (lt >> 1) & 1);
+      tc_fence_after();
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + buf * 256 + c0 + ((uint32_t)(wq * 32) << 16), v);
+        tmem_ld_wait();
+        if (c0 + 32 >= p.N) {     // last read of this accumulator: hand it back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (c0 + i < p.N) {
+            float x = v[i] + bias_s[c0 + i];
+            if (p.relu) x = fmaxf(x, 0.f);
+            if (ok) ob[(size_t)(c0 + i) * p.HW] = x;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 int taps_padded(int radius) { return (((2 * radius + 1) * (2 * radius + 1)) + 31) / 32 * 32; }
@@ -381,6 +515,42 @@ int b200corr_lookup_convc1_forward(const float *const *h_levels, int num_levels,
   }
 #undef LC1_LAUNCH
   B200_LAUNCH_OK("lookup_convc1_kernel");
+  return 0;
+}
+
+int b200corr_conv1x1_forward(const float *x, const float *weight, const float *bias, float *out, int B, int K,
+                             int N, int HW, int relu, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (B == 0) return 0;
+  B200_CHECK(x && weight && out, "conv1x1_forward: null pointer");
+  B200_CHECK(B > 0 && K >= 1 && N >= 1 && N <= 256 && HW >= 1, "conv1x1_forward: bad sizes (n_out <= 256)");
+  B200_CHECK(K % 4 == 0 && HW % 4 == 0, "conv1x1_forward: K and H*W must be multiples of 4 (16-byte TMA pitches)");
+  B200_CHECK((((uintptr_t)x | (uintptr_t)weight) & 15) == 0, "conv1x1_forward: operands must be 16-byte aligned");
+  cv::Params p;
+  p.B = B; p.K = K; p.N = N; p.NP = (N + 15) / 16 * 16; p.HW = HW; p.relu = relu; p.bias = bias; p.out = out;
+  p.tiles_per_b = (HW + cv::BM - 1) / cv::BM;
+  p.total_tiles = p.tiles_per_b * B;
+  p.kblocks = (K + cv::BK - 1) / cv::BK;
+  CUtensorMap mapX, mapW;
+  {
+    const uint64_t d[3] = {(uint64_t)HW, (uint64_t)K, (uint64_t)B};
+    const uint64_t s[3] = {4, (uint64_t)HW * 4, (uint64_t)HW * 4 * K};
+    const uint32_t box[3] = {32, 32, 1};
+    if (int e = b200::make_tensor_map(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, x, d, s, box,
+                                      CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return e;
+  }
+  {
+    const uint64_t d[3] = {(uint64_t)K, (uint64_t)N, 1};
+    const uint64_t s[3] = {4, (uint64_t)K * 4, (uint64_t)K * 4 * N};
+    const uint32_t box[3] = {32, (uint32_t)p.NP, 1};
+    if (int e = b200::make_tensor_map(&mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, weight, d, s, box,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return e;
+  }
+  static bool done[64];
+  if (int e = b200::set_max_smem_once((const void *)conv1x1_mn_kernel, cv::SMEM_BYTES, done)) return e;
+  const int grid = p.total_tiles < b200::num_sms() ? p.total_tiles : b200::num_sms();
+  conv1x1_mn_kernel<<<grid, cv::THREADS, cv::SMEM_BYTES, stream>>>(mapX, mapW, p);
+  B200_LAUNCH_OK("conv1x1_mn_kernel");
   return 0;
 }
 

@@ -26,6 +26,7 @@ import ctypes
 import math
 import os
 import types
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -151,10 +152,11 @@ def prepare_convc1(weight, num_levels, radius):
     if w2.shape[1] != num_levels * (2 * radius + 1) ** 2:
         raise RuntimeError(f"prepare_convc1: weight has {w2.shape[1]} input channels, expected "
                            f"{num_levels} * {(2 * radius + 1) ** 2}")
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), num_levels, radius, weight.device)
+    # cached per weight OBJECT (a weak reference guards against a recycled id / data pointer) and version counter
+    key = (id(weight), num_levels, radius)
     hit = _CONVC1_CACHE.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+        return hit[3]
     _require_cuda_f32("prepare_convc1", w2)
     L = _lib.lib()
     nbytes = L.b200corr_lookup_convc1_weight_bytes(num_levels, radius, n_out)
@@ -163,9 +165,9 @@ def prepare_convc1(weight, num_levels, radius):
         code = L.b200corr_lookup_convc1_prepare(_lib.ptr(w2), _lib.ptr(wp), num_levels, radius, n_out,
                                                 _lib.current_stream(w2.device))
     _lib.check(code, "b200corr_lookup_convc1_prepare")
-    if len(_CONVC1_CACHE) > 8:
-        _CONVC1_CACHE.clear()
-    _CONVC1_CACHE[key] = wp
+    for k in [k for k, v in _CONVC1_CACHE.items() if v[0]() is None]:     # weights that are gone
+        del _CONVC1_CACHE[k]
+    _CONVC1_CACHE[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), wp)
     return wp
 
 
@@ -186,6 +188,27 @@ def lookup_convc1_forward(levels, coords, wprep, bias, n_out, radius, H, W, mode
             _lib.ptr(bias) if bias is not None else None, _lib.ptr(out), B, H, W, radius, LOOKUP_MODES[mode], n_out,
             1 if relu else 0, _lib.current_stream(coords.device))
     _lib.check(code, "b200corr_lookup_convc1_forward")
+    return out
+
+
+def conv1x1_forward(x, weight, bias=None, relu=False):
+    """act(conv2d(x, weight (n_out, K, 1, 1), bias)) on the tensor cores (TF32), x read as it lies: (B, K, H, W) ->
+    (B, n_out, H, W).  The 1x1 convolution behind the lookup (models/raft/update.py:104,111)."""
+    x = x.contiguous()
+    n_out = weight.shape[0]
+    w2 = weight.detach().reshape(n_out, -1).contiguous().float()
+    _require_cuda_f32("conv1x1_forward", x, w2)
+    B, K, H, W = x.shape
+    if w2.shape[1] != K:
+        raise RuntimeError(f"conv1x1_forward: weight has {w2.shape[1]} input channels, x has {K}")
+    if bias is not None:
+        bias = bias.detach().contiguous().float()
+    out = torch.empty((B, n_out, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        code = _lib.lib().b200corr_conv1x1_forward(_lib.ptr(x), _lib.ptr(w2), _lib.ptr(bias) if bias is not None else None,
+                                                   _lib.ptr(out), B, K, n_out, H * W, 1 if relu else 0,
+                                                   _lib.current_stream(x.device))
+    _lib.check(code, "b200corr_conv1x1_forward")
     return out
 
 
@@ -485,11 +508,13 @@ class CorrBlock:
         return lookup_forward(self._levels, coords, self.radius, self.H, self.W, self.lookup_mode,
                               blocked_levels=self._blocked)
 
-    def lookup_convc1(self, coords, weight, bias=None, relu=True):
-        """`F.relu(convc1(self(coords)))` (models/raft/update.py:104,111 on top of raft.py:189) as ONE kernel: the
-        (B, L*(2r+1)^2, H, W) lookup result stays in shared memory / TMEM.  Inference path (no autograd through
-        the fused kernel): under grad mode with differentiable features or weights the unfused chain runs instead,
-        so gradients are always those of the reference."""
+    def lookup_convc1(self, coords, weight, bias=None, relu=True, impl=None):
+        """`F.relu(convc1(self(coords)))` (models/raft/update.py:104,111 on top of raft.py:189) on the tensor cores.
+        impl="fused": ONE kernel, the (B, L*(2r+1)^2, H, W) lookup result stays in shared memory / TMEM and never
+        touches HBM; impl="pipelined" (default, the faster one at RAFT's sizes): the plain lookup kernel followed by
+        a tcgen05 1x1-convolution kernel that reads the lookup result out of the L2.  B200CORR_LOOKUP_CONVC1
+        overrides the default.  Inference path: under grad mode with differentiable features or weights the
+        unfused reference chain runs instead, so gradients are always those of the reference."""
         coords = coords.detach().float()
         n_out = weight.shape[0]
         needs_grad = torch.is_grad_enabled() and (self._handle is not None or weight.requires_grad or
@@ -499,6 +524,19 @@ class CorrBlock:
         if not fused_ok:
             out = F.conv2d(self(coords), weight.reshape(n_out, -1, 1, 1), bias)
             return F.relu(out) if relu else out
+        if impl is None:
+            impl = os.environ.get("B200CORR_LOOKUP_CONVC1", "pipelined")
+        nin = self.num_levels * (2 * self.radius + 1) ** 2
+        if impl == "pipelined" and nin % 4 == 0 and (self.H * self.W) % 4 == 0:
+            # two kernels: the plain lookup, then the convolution as a tcgen05 GEMM reading the lookup result from
+            # the L2 (chunks of 4 samples: 39.8 MB at 48x160, well inside the 126 MB L2)
+            outs = []
+            for b0 in range(0, self.B, 4):
+                sl = slice(b0 * self.H * self.W, min(self.B, b0 + 4) * self.H * self.W)
+                corr = lookup_forward([v[sl] for v in self._levels], coords[b0:b0 + 4], self.radius, self.H, self.W,
+                                      self.lookup_mode, blocked_levels=self._blocked)
+                outs.append(conv1x1_forward(corr, weight, bias, relu))
+            return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         wp = prepare_convc1(weight, self.num_levels, self.radius)
         return lookup_convc1_forward(self._levels, coords, wp, bias, n_out, self.radius, self.H, self.W,
                                      self.lookup_mode, self._blocked, relu)
