@@ -317,11 +317,11 @@ lookup_convc1_kernel(const __grid_constant__ CUtensorMap mapW, const fz::Params 
 // the 39.8 MB of X are still in the 126 MB L2 when this kernel reads them.  TMEM holds two accumulators so that
 // the epilogue (bias, ReLU, coalesced stores: lane = query) of a tile overlaps the MMAs of the next.
 namespace cv {
-constexpr int BM = 128, BK = 32, NST = 4, THREADS = 192;
-constexpr int A_BYTES = BM * BK * 4, B_BYTES = 256 * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BM = 128, BK = 32, NST = 3, THREADS = 320;      // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
+constexpr int A_BYTES = 2 * BM * BK * 4, B_BYTES = 256 * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = 1024 + NST * STAGE_BYTES + 256;
 struct Params {
-  int B, K, N, NP, HW, tiles_per_b, total_tiles, kblocks, relu;   // NP = N rounded up to 16
+  int B, K, N, NP, HW, pairs_per_b, total_pairs, kblocks, relu;   // NP = N rounded up to 16
   const float *bias;
   float *out;
 };
@@ -331,6 +331,9 @@ __device__ __forceinline__ uint64_t desc_mnmajor_sw128_32b(uint32_t smem_addr, u
 }
 }  // namespace cv
 
+// One CTA = a PAIR of 128-query tiles (256 queries, two TMEM accumulators): every 32-channel block of the weights
+// (32 KB through the L2 per load) then serves 256 queries -- with single tiles the weight re-reads were 60 % of
+// this kernel's L2->SM traffic and the MMA thread sat on the TMA barrier (ncu: tensor pipe 19 % active).
 __global__ void __launch_bounds__(cv::THREADS, 1)
 conv1x1_mn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const cv::Params p) {
   using namespace cv;
@@ -339,8 +342,8 @@ conv1x1_mn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *sm = smem_raw + (base - raw);
   uint64_t *bars = reinterpret_cast<uint64_t *>(sm + NST * STAGE_BYTES);
-  uint64_t *full_bar = bars, *empty_bar = bars + NST, *tfull = bars + 2 * NST, *tempty = tfull + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfull + 4);
+  uint64_t *full_bar = bars, *empty_bar = bars + NST, *tfull = bars + 2 * NST;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfull + 1);
   __shared__ float bias_s[256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 256; i += THREADS) bias_s[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
@@ -351,10 +354,7 @@ conv1x1_mn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);
-    }
+    mbar_init(tfull, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -365,72 +365,58 @@ conv1x1_mn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int pr = blockIdx.x;                        // one pair per CTA
+  const int b = pr / p.pairs_per_b, m0 = (pr - b * p.pairs_per_b) * (2 * BM);
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int b = t / p.tiles_per_b, m0 = (t - b * p.tiles_per_b) * BM;
-        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-          const int st = it % NST;
-          mbar_wait(&empty_bar[st], ((it / NST) & 1) ^ 1);
-          uint8_t *a = sm + st * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[st], A_BYTES + (uint32_t)p.NP * BK * 4);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        const int st = kb % NST;
+        mbar_wait(&empty_bar[st], ((kb / NST) & 1) ^ 1);
+        uint8_t *a = sm + st * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[st], A_BYTES + (uint32_t)p.NP * BK * 4);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_3d(a + j * 4096, &mapX, &full_bar[st], m0 + 32 * j, kb * BK, b);
-          tma_load_3d(a + A_BYTES, &mapW, &full_bar[st], kb * BK, 0, 0);
-        }
+        for (int j = 0; j < 8; ++j) tma_load_3d(a + j * 4096, &mapX, &full_bar[st], m0 + 32 * j, kb * BK, b);
+        tma_load_3d(a + A_BYTES, &mapW, &full_bar[st], kb * BK, 0, 0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(BM, p.NP) | (1u << 15);      // A MN-major
-      uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
-        const int buf = lt & 1;
-        mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        const int st = kb % NST;
+        mbar_wait(&full_bar[st], (kb / NST) & 1);
         tc_fence_after();
-        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-          const int st = it % NST;
-          mbar_wait(&full_bar[st], (it / NST) & 1);
-          tc_fence_after();
-          const uint32_t a_addr = base + st * STAGE_BYTES;
-          const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + A_BYTES);
+        const uint32_t a_addr = base + st * STAGE_BYTES;
+        const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + A_BYTES);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
-            umma_tf32(tmem_base + buf * 256, desc_mnmajor_sw128_32b(a_addr + k4 * 1024, 4096, 512), bdesc + 2 * k4, idesc,
-                      (kb | k4) != 0);
-          umma_commit(&empty_bar[st]);
-        }
-        umma_commit(&tfull[buf]);
+            umma_tf32(tmem_base + h * 256, desc_mnmajor_sw128_32b(a_addr + h * 16384 + k4 * 1024, 4096, 512),
+                      bdesc + 2 * k4, idesc, (kb | k4) != 0);
+        umma_commit(&empty_bar[st]);
       }
+      umma_commit(tfull);
     }
   } else {
-    const int wq = warp & 3;
-    uint32_t lt = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
-      const int buf = lt & 1;
-      const int b = t / p.tiles_per_b, q = (t - b * p.tiles_per_b) * BM + wq * 32 + lane;
-      const bool ok = q < p.HW;
-      float *ob = p.out + ((size_t)b * p.N) * p.HW + q;
-      mbar_wait(&tfull[buf], (lt >> 1) & 1);
-      tc_fence_after();
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
-        float v[32];
-        tmem_ld_32x32(tmem_base + buf * 256 + c0 + ((uint32_t)(wq * 32) << 16), v);
-        tmem_ld_wait();
-        if (c0 + 32 >= p.N) {     // last read of this accumulator: hand it back before the stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[buf]);
-        }
+    // epilogue: warps 2..9; warp w reads TMEM lane quarter w % 4 of accumulator (w - 2) / 4
+    const int wq = warp & 3, h = (warp - 2) >> 2;
+    const int q = m0 + h * BM + wq * 32 + lane;
+    const bool ok = q < p.HW;
+    float *ob = p.out + ((size_t)b * p.N) * p.HW + q;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.N; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + h * 256 + c0 + ((uint32_t)(wq * 32) << 16), v);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (c0 + i < p.N) {
-            float x = v[i] + bias_s[c0 + i];
-            if (p.relu) x = fmaxf(x, 0.f);
-            if (ok) ob[(size_t)(c0 + i) * p.HW] = x;
-          }
+      for (int i = 0; i < 32; ++i) {
+        if (c0 + i < p.N) {
+          float x = v[i] + bias_s[c0 + i];
+          if (p.relu) x = fmaxf(x, 0.f);
+          if (ok) ob[(size_t)(c0 + i) * p.HW] = x;
         }
       }
     }
@@ -528,8 +514,8 @@ int b200corr_conv1x1_forward(const float *x, const float *weight, const float *b
   B200_CHECK((((uintptr_t)x | (uintptr_t)weight) & 15) == 0, "conv1x1_forward: operands must be 16-byte aligned");
   cv::Params p;
   p.B = B; p.K = K; p.N = N; p.NP = (N + 15) / 16 * 16; p.HW = HW; p.relu = relu; p.bias = bias; p.out = out;
-  p.tiles_per_b = (HW + cv::BM - 1) / cv::BM;
-  p.total_tiles = p.tiles_per_b * B;
+  p.pairs_per_b = (HW + 2 * cv::BM - 1) / (2 * cv::BM);
+  p.total_pairs = p.pairs_per_b * B;
   p.kblocks = (K + cv::BK - 1) / cv::BK;
   CUtensorMap mapX, mapW;
   {
@@ -548,8 +534,7 @@ int b200corr_conv1x1_forward(const float *x, const float *weight, const float *b
   }
   static bool done[64];
   if (int e = b200::set_max_smem_once((const void *)conv1x1_mn_kernel, cv::SMEM_BYTES, done)) return e;
-  const int grid = p.total_tiles < b200::num_sms() ? p.total_tiles : b200::num_sms();
-  conv1x1_mn_kernel<<<grid, cv::THREADS, cv::SMEM_BYTES, stream>>>(mapX, mapW, p);
+  conv1x1_mn_kernel<<<p.total_pairs, cv::THREADS, cv::SMEM_BYTES, stream>>>(mapX, mapW, p);
   B200_LAUNCH_OK("conv1x1_mn_kernel");
   return 0;
 }

@@ -20,7 +20,7 @@
 //     (MODE 1), N = channels, K in blocks of 32 through a 4-stage TMA ring; the operands are the fp32 tensors
 //     themselves (the tensor core reads the upper 19 bits: TF32 by truncation), G_l straight from the gradient
 //     pyramid -- K-major for dF1, MN-major for the transposed product (no transposed copy of a 1 GB tensor).
-//     Work items are split along K so that 148 SMs get ~5 equal waves; partial sums land with red.global.add.
+//     Work items (256 rows) are split along K so that 148 SMs get ~5 equal waves; partial sums land with red.global.add.
 //   * gemm_nt_simt_kernel: exact fp32 (precision "fp32", and every shape the tensor maps cannot express).
 #include <cstdlib>
 #include <cstring>
@@ -132,10 +132,13 @@ gemm_nt_simt_kernel(const SimtGemm g) {
 
 // ------------------------------------------------------------------------------ tcgen05 GEMM
 namespace vb {
-constexpr int BM = 128, BK = 32, NST = 4, THREADS = 192, TMEM_COLS = 256;
-constexpr int A_BYTES = BM * BK * 4, B_BYTES = 256 * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+// One work item covers TWO 128-row MMA tiles (256 rows, two TMEM accumulators) so that every 32 KB block of the
+// N operand (the feature map) fetched through the L2 serves 256 rows: with single tiles the feature-map re-reads
+// were two thirds of the L2->SM traffic (3.7 GB per product at B=4) and the kernels ran at 0.30 / 0.33 ms.
+constexpr int BM = 128, TM = 2 * BM, BK = 32, NST = 3, THREADS = 320, TMEM_COLS = 512;
+constexpr int A_BYTES = TM * BK * 4, B_BYTES = 256 * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = 1024 + NST * STAGE_BYTES + 256;
-constexpr int KSPLIT = 3;
+constexpr int KSPLIT = 6;
 
 struct Maps {
   CUtensorMap a[kMaxLv];   // gradient level l: (HW_l, HW, B)
@@ -199,7 +202,7 @@ volgrad_tc_kernel(const __grid_constant__ vb::Maps maps, const vb::Params p) {
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 4);
+    mbar_init(acc_empty, 8);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -216,7 +219,7 @@ volgrad_tc_kernel(const __grid_constant__ vb::Maps maps, const vb::Params p) {
     if (MODE == 0) {
       split = item % KSPLIT;
       const int t = item / KSPLIT;
-      m0 = (t % p.mtiles0) * BM;
+      m0 = (t % p.mtiles0) * TM;
       b = t / p.mtiles0;
       lvl = 0;
     } else {
@@ -225,7 +228,7 @@ volgrad_tc_kernel(const __grid_constant__ vb::Maps maps, const vb::Params p) {
       int r = item - p.prefix[lvl];
       split = r % KSPLIT;
       r /= KSPLIT;
-      m0 = (r % p.mtiles[lvl]) * BM;
+      m0 = (r % p.mtiles[lvl]) * TM;
       b = r / p.mtiles[lvl];
     }
   };
@@ -254,10 +257,11 @@ volgrad_tc_kernel(const __grid_constant__ vb::Maps maps, const vb::Params p) {
           mbar_arrive_expect_tx(&full_bar[st], A_BYTES + (uint32_t)p.N * BK * 4);
           if (MODE == 0) {
             tma_load_3d(a, &maps.a[l], &full_bar[st], kb * BK, m0, b);              // G_l rows = queries, K = keys
+            tma_load_3d(a + 16384, &maps.a[l], &full_bar[st], kb * BK, m0 + BM, b);
             tma_load_3d(a + A_BYTES, &maps.b[l], &full_bar[st], kb * BK, 0, b);     // pool_l(F2): rows = channels
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)                                             // G_l: K = queries (rows), M = keys
+            for (int j = 0; j < 8; ++j)                                             // G_l: K = queries (rows), M = keys
               tma_load_3d(a + j * 4096, &maps.a[l], &full_bar[st], m0 + 32 * j, kb * BK, b);
             tma_load_3d(a + A_BYTES, &maps.b[0], &full_bar[st], kb * BK, 0, b);     // F1: rows = channels, K = queries
           }
@@ -289,25 +293,27 @@ volgrad_tc_kernel(const __grid_constant__ vb::Maps maps, const vb::Params p) {
           const uint32_t a_addr = base + st * STAGE_BYTES;
           const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + A_BYTES);
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint64_t adesc = MODE == 0 ? umma_desc_kmajor_sw128(a_addr) + 2 * k4
-                                             : umma_desc_mnmajor_sw128_32b(a_addr + k4 * 1024, 4096, 512);
-            umma_tf32(tmem_base, adesc, bdesc + 2 * k4, idesc, (kb | k4) != 0);
-          }
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t adesc = MODE == 0 ? umma_desc_kmajor_sw128(a_addr + h * 16384) + 2 * k4
+                                               : umma_desc_mnmajor_sw128_32b(a_addr + h * 16384 + k4 * 1024, 4096, 512);
+              umma_tf32(tmem_base + h * 256, adesc, bdesc + 2 * k4, idesc, (kb | k4) != 0);
+            }
           umma_commit(&empty_bar[st]);
         }
         umma_commit(acc_full);
       }
     }
   } else {
-    // ================= epilogue: warps 2..5 cover the four TMEM lane quarters
-    const int wq = warp & 3;
+    // ================= epilogue: warps 2..9 = (accumulator h, TMEM lane quarter)
+    const int wq = warp & 3, h = (warp - 2) >> 2;
     uint32_t ic = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++ic) {
       int lvl, b, m0, split;
       decode(item, lvl, b, m0, split);
       const int n = item_kblocks(split);
-      const int m = m0 + wq * 32 + lane;
+      const int m = m0 + h * BM + wq * 32 + lane;
       const int mlim = MODE == 0 ? p.HW : p.HWl[lvl];
       float *out = (MODE == 0 ? p.out[0] : p.out[lvl]) + (size_t)b * p.C * mlim + m;
       mbar_wait(acc_full, ic & 1);
@@ -315,7 +321,7 @@ volgrad_tc_kernel(const __grid_constant__ vb::Maps maps, const vb::Params p) {
       if (n > 0) {
         for (int c0 = 0; c0 < p.C; c0 += 32) {
           float v[32];
-          tmem_ld_32x32(tmem_base + c0 + ((uint32_t)(wq * 32) << 16), v);
+          tmem_ld_32x32(tmem_base + h * 256 + c0 + ((uint32_t)(wq * 32) << 16), v);
           tmem_ld_wait();
           if (m < mlim) {
 #pragma unroll
@@ -439,7 +445,7 @@ int b200corr_volume_backward(const float *const *h_grad_levels, int num_levels, 
       p.HWl[l] = HWl[l];
       const uint64_t dg[3] = {(uint64_t)HWl[l], (uint64_t)HW, (uint64_t)B};
       const uint64_t sg[3] = {4, (uint64_t)HWl[l] * 4, (uint64_t)HWl[l] * 4 * HW};
-      const uint32_t box_k[3] = {32, 128, 1};     // MODE 0: 128 query rows x 32 keys (K-major)
+      const uint32_t box_k[3] = {32, 128, 1};     // MODE 0: 128 query rows x 32 keys (K-major), two boxes per stage
       const uint32_t box_mn[3] = {32, 32, 1};     // MODE 1: 32 query rows (K) x 32 keys (M, contiguous)
       if (int e = b200::make_tensor_map(&m0.a[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h_grad_levels[l], dg, sg, box_k,
                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)) return e;
@@ -461,7 +467,7 @@ int b200corr_volume_backward(const float *const *h_grad_levels, int num_levels, 
     // ---- MODE 0: K = the keys of all levels, cut into KSPLIT runs of equal length
     Params p0 = p;
     p0.out[0] = grad_fmap1;
-    p0.mtiles0 = (HW + BM - 1) / BM;
+    p0.mtiles0 = (HW + TM - 1) / TM;
     {
       int kbl[kMaxLv], total = 0;
       for (int l = 0; l < num_levels; ++l) { kbl[l] = (HWl[l] + BK - 1) / BK; total += kbl[l]; }
@@ -492,7 +498,7 @@ int b200corr_volume_backward(const float *const *h_grad_levels, int num_levels, 
     int items = 0;
     for (int l = 0; l < num_levels; ++l) {
       p1.out[l] = g2p[l];
-      p1.mtiles[l] = (HWl[l] + BM - 1) / BM;
+      p1.mtiles[l] = (HWl[l] + TM - 1) / TM;
       p1.prefix[l] = items;
       items += B * p1.mtiles[l] * KSPLIT;
     }
