@@ -410,7 +410,12 @@ class _LookupFunction(torch.autograd.Function):
 
 
 class CorrBlock:
-    """models/raft/corr.py:26-106."""
+    """models/raft/corr.py:26-106.
+
+    Note on `corr_pyramid` / `get_corr_pyramid()`: they hand out the raw pyramid buffers (for the blocked layout a
+    de-blocked copy of the two fine levels), WITHOUT an autograd graph -- in the reference these are differentiable
+    matmul / avg_pool2d outputs (raft.py:161-163 exposes them through return_feat_maps).  A loss built on them gets
+    no gradient; gradients flow through the lookups (`__call__`), whose coordinates are detached as in raft.py:188."""
 
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, compute_spatial=False, precision=None,
                  lookup_mode="grid_sample", layout="auto", backward_precision=None):
