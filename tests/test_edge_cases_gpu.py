@@ -138,3 +138,89 @@ def test_caller_owned_output_buffers_and_host_pipeline():
         o = backend.forward(h[0].cuda(), h[1].cuda(), *q)
         x1, x2 = backend.backward(h[0].cuda(), h[1].cuda(), h[2].cuda(), *q)
         assert torch.equal(h[3].cuda(), o) and torch.equal(h[4].cuda(), x1) and torch.equal(h[5].cuda(), x2)
+
+
+def test_round2_entry_points_empty_batch_errors_and_graph_capture():
+    """The round-2 entry points (volume backward, lookup -> convc1 in both variants, 1x1 conv, patch placement):
+    empty batch, loud failure on CPU tensors, CUDA-graph capture + replay gives the eager values."""
+    import math
+
+    import torch.nn.functional as F
+    from understanding_flow_robustness_b200 import CorrBlock, attack, coords_grid, raft_corr
+    # ---- empty batch
+    f0 = torch.zeros(0, 16, 8, 8, device="cuda")
+    g0 = [torch.zeros(0, 1, 8 >> l, 8 >> l, device="cuda") for l in range(3)]
+    d1, d2 = raft_corr.volume_backward(g0, f0, f0, 0.25, "tf32")
+    assert tuple(d1.shape) == tuple(d2.shape) == (0, 16, 8, 8)
+    w = torch.randn(32, 3 * 25, device="cuda")
+    c0 = torch.zeros(0, 2, 8, 8, device="cuda")
+    assert tuple(CorrBlock(f0, f0, 3, 2).lookup_convc1(c0, w, None).shape) == (0, 32, 8, 8)
+    assert tuple(raft_corr.conv1x1_forward(torch.zeros(0, 8, 4, 4, device="cuda"), torch.randn(32, 8, device="cuda")).shape) == (0, 32, 4, 4)
+    i0 = torch.zeros(0, 3, 16, 16, device="cuda")
+    pt = torch.rand(1, 3, 8, 8, device="cuda", requires_grad=True)
+    a1, a2 = attack.compose_cuda(i0, i0, pt, torch.ones(1, 1, 8, 8, device="cuda"), torch.zeros(0, 5, device="cuda"))
+    (a1.sum() + a2.sum()).backward()
+    assert tuple(a1.shape) == (0, 3, 16, 16) and float(pt.grad.abs().max()) == 0.0
+    # ---- CPU tensors are refused (no fallback)
+    with pytest.raises(RuntimeError):
+        raft_corr.conv1x1_forward(torch.zeros(1, 8, 4, 4), torch.zeros(32, 8))
+    with pytest.raises(RuntimeError):
+        raft_corr.volume_backward([torch.zeros(64, 1, 8, 8)], torch.zeros(1, 16, 8, 8), torch.zeros(1, 16, 8, 8), 0.25, "fp32")
+    with pytest.raises(RuntimeError):
+        attack.compose_cuda(torch.zeros(1, 3, 16, 16), torch.zeros(1, 3, 16, 16), torch.zeros(1, 3, 8, 8), torch.ones(1, 1, 8, 8),
+                            torch.zeros(1, 5))
+    with pytest.raises(RuntimeError):        # unsupported channel count of the fused kernel's C ABI: loud, not silent
+        raft_corr.lookup_convc1_forward([torch.zeros(64, 1, 8, 8, device="cuda")], torch.zeros(1, 2, 8, 8, device="cuda"),
+                                        torch.zeros(1 * 24 * 32, device="cuda"), None, 24, 2, 8, 8)
+    # ---- graph capture
+    torch.manual_seed(0)
+    B, C, H, W = 1, 32, 16, 32
+    f1 = torch.randn(B, C, H, W, device="cuda")
+    f2 = torch.randn(B, C, H, W, device="cuda")
+    conv = torch.nn.Conv2d(4 * 81, 128, 1).cuda()
+    glv = [torch.randn(B * H * W, 1, H >> l, W >> l, device="cuda") for l in range(4)]
+    coords = coords_grid(B, H, W, "cuda") + torch.randn(B, 2, H, W, device="cuda")
+    with torch.no_grad():
+        blk = CorrBlock(f1, f2, 4, 4, precision="tf32")
+
+        def work():
+            return (blk.lookup_convc1(coords, conv.weight, conv.bias, impl="fused"),
+                    blk.lookup_convc1(coords, conv.weight, conv.bias, impl="pipelined"),
+                    *raft_corr.volume_backward(glv, f1, f2, 1 / math.sqrt(C), "fp32"))
+        eager = [t.clone() for t in work()]
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            outs = work()
+        coords.add_(0.0)
+        g.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(outs, eager):
+            assert torch.equal(a, b)
+        # fused vs pipelined differ only by rounding vs truncation of the operands
+        assert float((eager[0] - eager[1]).abs().max()) <= 2.0 ** -8 * float(F.conv2d(blk(coords).abs(), conv.weight.abs()).max())
+
+
+@pytest.mark.parametrize("B,K,N,H,W", [(1, 324, 256, 48, 160), (2, 196, 96, 13, 20), (3, 8, 32, 5, 4), (1, 100, 64, 9, 28),
+                                       (1, 324, 256, 7, 36), (2, 40, 128, 16, 17 * 4)])
+def test_conv1x1_tensor_core_kernel_vs_torch(B, K, N, H, W):
+    """b200corr_conv1x1_forward (tcgen05, MN-major operand, tile pairs, ragged K / HW / N) against F.conv2d of the
+    TF32-truncated operands."""
+    import torch.nn.functional as F
+    from understanding_flow_robustness_b200 import raft_corr
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = torch.Generator(device="cuda").manual_seed(K + N)
+        x = torch.randn(B, K, H, W, device="cuda", generator=g)
+        w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+        bias = torch.randn(N, device="cuda", generator=g)
+        tr = lambda t: (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+        for relu in (False, True):
+            got = raft_corr.conv1x1_forward(x, w, bias, relu=relu)
+            ref = F.conv2d(tr(x), tr(w).view(N, K, 1, 1), bias)
+            ref = F.relu(ref) if relu else ref
+            assert got.shape == ref.shape
+            assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev

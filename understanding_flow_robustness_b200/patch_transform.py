@@ -62,7 +62,6 @@ class ComposeFunction(Function):
         _lib.check(code, "b200corr_patch_compose_forward")
         ctx.save_for_backward(img1, img2, patch_c, mask_c, pl)
         ctx.patch_shape = patch.shape
-        ctx.mark_non_differentiable()
         return adv1, adv2
 
     @staticmethod
@@ -71,6 +70,8 @@ class ComposeFunction(Function):
         img1, img2, patch, mask, pl = ctx.saved_tensors
         n, _, H, W = img1.shape
         p = patch.shape[-1]
+        if n == 0:                       # no pairs: no contribution (strides of empty tensors carry no layout)
+            return None, None, torch.zeros(ctx.patch_shape, dtype=torch.float32, device=patch.device), None, None
         fmt = torch.contiguous_format if img1.is_contiguous() else torch.channels_last
         g1 = g1.contiguous(memory_format=fmt)
         g2 = g2.contiguous(memory_format=fmt)
