@@ -1050,6 +1050,16 @@ def raft_bench(dev):
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    tr = {}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "raft_traffic.json")))
+    except Exception:
+        pass
+
+    def traffic(kernel):
+        r_, w_ = tr.get(kernel + "_dram_read_bytes"), tr.get(kernel + "_dram_write_bytes")
+        return None if r_ is None else {"dram_read": r_, "dram_write": w_, "source": tr.get("source"),
+                                        "note": "writes still dirty in the 126 MB L2 when the launch ends are not counted by ncu"}
     return {"metric": "RAFT corr+lookup ms/iter", "ms_per_iter": (build_ms + c["iters"] * look_ms) / c["iters"],
             "build_ms": build_ms, "lookup_ms": look_ms,
             "volume_layout": {"blocked_levels_mask": layout_mask,
@@ -1066,10 +1076,15 @@ def raft_bench(dev):
             "timed_loop": {"build": how_build, "lookups": how_look},
             "roofline_build": {"bound": "hbm", "achieved": vol_bytes / (build_ms * 1e-3) / 1e9, "peak": hbm,
                                "unit": "GB/s", "frac": vol_bytes / (build_ms * 1e-3) / 1e9 / hbm, "peak_source": src,
-                               "bytes": "volume + 3 pooled levels written once + features read once"},
+                               "bytes": "volume + 3 pooled levels written once + features read once",
+                               "traffic": traffic("allpairs_tc_kernel")},
             "roofline_lookup": {"bound": "hbm", "achieved": look_bytes / (look_ms * 1e-3) / 1e9, "peak": hbm,
                                 "unit": "GB/s", "frac": look_bytes / (look_ms * 1e-3) / 1e9 / hbm, "peak_source": src,
-                                "bytes": "324-channel output written + 4 levels x 10x10 window read per query"},
+                                "bytes": "324-channel output written + 4 levels x 10x10 window read per query",
+                                "traffic": traffic("lookup_fwd_kernel"),
+                                "gather_bound": "scripts/probes/gather_probe2.cu: the window bytes of one lookup alone take 21.3 us "
+                                                "(3.7 TB/s of requested bytes) whatever the request shape; + the result at the copy "
+                                                "peak = 27.4 us (DESIGN.md 2.6)"},
             "roofline": {"bound": "hbm", "what": "(build + 12 lookups) / 12 against the algorithmic bytes of both at the HBM copy peak",
                          "bound_ms_per_iter": (vol_bytes + c["iters"] * look_bytes) / (hbm * 1e9) * 1e3 / c["iters"],
                          "frac": (vol_bytes + c["iters"] * look_bytes) / (hbm * 1e9) * 1e3 / (build_ms + c["iters"] * look_ms)}}

@@ -82,6 +82,27 @@ if os.path.exists(rep):
     tr["source"] = f"profiles/{R}_sampler_full_summary.txt (ncu --set full, B=8, 256x48x160)"
     json.dump(tr, open(os.path.join(P, "sampler_traffic.json"), "w"), indent=1)
 
+# ---- DRAM traffic of the RAFT kernels per launch (bench.py's raft.roofline_build / roofline_lookup .traffic)
+rep = os.path.join(G, f"{R}_raft_full.ncu-rep")
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rr[0], rr[1], rr[2:]
+
+    def val2(row, key):
+        i = hdr.index(key)
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+        return float(row[i].replace(",", "")) * mult
+
+    ki = hdr.index("Kernel Name")
+    tr = {"source": f"profiles/{R}_raft_full_summary.txt (ncu --set full, B=4, 256x48x160; cold L2, one launch each)"}
+    for key, pat in (("allpairs_tc_kernel", "allpairs_tc"), ("lookup_fwd_kernel", "lookup_fwd")):
+        rows_k = [r for r in data if pat in r[ki]]
+        if rows_k:
+            tr[key + "_dram_read_bytes"] = sum(val2(r, "dram__bytes_read.sum") for r in rows_k) / len(rows_k)
+            tr[key + "_dram_write_bytes"] = sum(val2(r, "dram__bytes_write.sum") for r in rows_k) / len(rows_k)
+    json.dump(tr, open(os.path.join(P, "raft_traffic.json"), "w"), indent=1)
+
 for f in (f"{R}_bench_line.json", f"{R}_vs_reference_cuda.json", f"{R}_sweep_cfg5.json", f"{R}_attack_timeline_g1.json",
           f"{R}_attack_timeline_g8.json", f"{R}_bench_line_g2.json", f"{R}_bench_line_g8.json"):
     if os.path.exists(os.path.join(G, f)):
