@@ -34,6 +34,10 @@
 // (raft.py:188 detaches them).
 #include "raft_lookup.cuh"
 
+#ifndef B200_LOOKUP_BWD_RED
+#define B200_LOOKUP_BWD_RED 1     // 73.9 -> 71.2 us per lookup backward at B=4 (scripts/time_lookup_bwd_variants.py); 0 = read-modify-write
+#endif
+
 namespace {
 using namespace b200lookup;
 
@@ -377,13 +381,34 @@ lookup_bwd_kernel(const LookupParams p, const float *__restrict__ coords,
     // all sector loads of this warp's rows first, then the adds and the stores
     SectorPlan<RPW, WS> sp;
     sp.make(slice, warp, oy, ox, LH, LW, ylo, yhi, clo, chi);
+    const int off = ox & 4;
+#if B200_LOOKUP_BWD_RED
+    // fire-and-forget vector reductions at the L2 instead of load -> add -> store through the SM: every address is
+    // still added to by exactly one lane per launch (launches are stream-ordered), so the sums stay deterministic
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const float *wrow = wl + ((warp * RPW + r) * kCols) * 32;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        if (!sp.ok[r][g]) continue;
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int sidx = 8 * g + k - off;
+          a[k] = (sidx >= 0 && sidx < kCols) ? wrow[sidx * 32] : 0.f;
+        }
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(sp.ptr[r][g]), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(sp.ptr[r][g] + 4), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]) : "memory");
+      }
+    }
+    return;
+#endif
     float v[RPW][3][8];
 #pragma unroll
     for (int r = 0; r < RPW; ++r)
 #pragma unroll
       for (int g = 0; g < 3; ++g)
         if (sp.ok[r][g]) ld256_sched(sp.ptr[r][g], v[r][g]);
-    const int off = ox & 4;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       const float *wrow = wl + ((warp * RPW + r) * kCols) * 32;
