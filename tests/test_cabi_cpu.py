@@ -47,6 +47,64 @@ def test_host_only_entry_points(lib):
     assert f(1, 8, 12, 13, 1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1, 0, 0) == 0    # W % 4 != 0
 
 
+def _backward_plan(lib, B, C, H, W, hyper, env):
+    """The host-side schedule of the backward units: (offsets[grid + 1], unit ids)."""
+    import ctypes
+    import numpy as np
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        lib.b200corr_sampler_backward_workspace_bytes.restype = ctypes.c_size_t
+        n = lib.b200corr_sampler_backward_workspace_bytes(B, C, H, W, *hyper, 0)
+        buf = np.zeros(n // 4, dtype=np.int32)
+        assert lib.b200corr_sampler_backward_plan(B, C, H, W, *hyper, 0, buf.ctypes.data_as(ctypes.c_void_p),
+                                                  ctypes.c_size_t(n)) == 0
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return buf
+
+
+@pytest.mark.parametrize("B,H,W,C", [(1, 48, 160, 256), (4, 48, 160, 256), (8, 48, 160, 256), (8, 55, 128, 256),
+                                     (3, 68, 120, 256), (8, 24, 80, 96)])
+def test_backward_plan_is_a_balanced_permutation(lib, B, H, W, C):
+    """b200corr_sampler_backward_plan: every unit exactly once; the refined schedule is never worse than plain
+    longest-processing-time-first and reaches the optimum of the BASELINE config-2 shape (118 source rows per CTA
+    against a mean of 116.8; LPT alone: 122)."""
+    hyper = (1, 1, 21, 21, 0, 0, 1, 1, 2, 2, 1, 1)
+    grid_full = 148     # num_sms() without a device
+
+    def rows_of_groups():
+        # source rows a unit of each row group walks (sampler_fast_bwd.cu: bwd_group_steps), radius 10, dpH 2
+        out = []
+        for rp in range(2):
+            ns = (H - rp + 1) // 2
+            for s0 in range(0, ns, 4):
+                s_last = min(s0 + 3, ns - 1)
+                out.append(min(s_last + 10, ns - 1) - max(s0 - 10, 0) + 1)
+        return out
+
+    cost = rows_of_groups()
+    per_group = ((W + 31) // 32) * ((C + 127) // 128 if C % 128 == 0 else (C + 31) // 32)
+    per_sample = len(cost) * per_group
+    total = B * per_sample
+    grid = min(grid_full, total)
+    spans = {}
+    for name, env in (("lpt", {"B200CORR_BWD_PLAN_LS": "0"}), ("refined", {"B200CORR_BWD_PLAN_LS": "1"})):
+        buf = _backward_plan(lib, B, C, H, W, hyper, env)
+        assert len(buf) == grid + 1 + total
+        offs, ids = buf[:grid + 1], buf[grid + 1:]
+        assert offs[0] == 0 and offs[grid] == total and all(offs[i] <= offs[i + 1] for i in range(grid))
+        assert sorted(ids.tolist()) == list(range(total))
+        spans[name] = max(sum(cost[(u % per_sample) // per_group] for u in ids[offs[c]:offs[c + 1]]) for c in range(grid))
+    assert spans["refined"] <= spans["lpt"]
+    if (B, H, W, C) == (8, 48, 160, 256):
+        assert spans == {"lpt": 122, "refined": 118}
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "understanding_flow_robustness_b200")
     for dirpath, _, files in os.walk(pkg):

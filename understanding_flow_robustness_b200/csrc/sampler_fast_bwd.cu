@@ -19,6 +19,7 @@
 // Source rows outside the image are never visited, so work tracks the in-bounds MAC count.
 // Persistent CTAs, one per SM, a TMA/mbarrier ring over source rows that runs across units.
 #include <algorithm>
+#include <cstdlib>
 #include <queue>
 #include <vector>
 
@@ -354,6 +355,8 @@ int bwd_group_steps(const BwdParams &p, int gi) {
   return Rhi - Rlo + 1;
 }
 
+constexpr int kBwdUnitOverheadRows = 0;
+
 static inline int bwd_grid(int total_units) {
   return total_units < b200::num_sms() ? total_units : b200::num_sms();
 }
@@ -370,6 +373,11 @@ int bwd_plan(int B, int C, int H, int W, int dpH, int grid, int *h_plan, size_t 
   for (int gi = 0; gi < p.g.ngroups; ++gi) cost[gi] = bwd_group_steps<Cfg>(p, gi);
   std::vector<int> units(p.total_units);
   for (int u = 0; u < p.total_units; ++u) units[u] = u;
+  // cost of a unit = the source rows it walks + a fixed part (drain of the accumulators, stores, ring turn-around)
+  // worth B200CORR_BWD_UNIT_OVERHEAD rows (default below: fitted on a B200, scripts/time_bwd_plan.py)
+  int overhead = kBwdUnitOverheadRows;
+  if (const char *e = getenv("B200CORR_BWD_UNIT_OVERHEAD")) overhead = atoi(e);
+  for (int &c : cost) c += overhead;
   auto cost_of = [&](int u) { return cost[(u % p.g.units_per_sample) / per_group]; };
   std::stable_sort(units.begin(), units.end(), [&](int a, int b) { return cost_of(a) > cost_of(b); });
   using Bin = std::pair<long long, int>;  // (load, cta)
@@ -381,6 +389,57 @@ int bwd_plan(int B, int C, int H, int W, int dpH, int grid, int *h_plan, size_t 
     heap.pop();
     lists[b.second].push_back(u);
     heap.push({b.first + cost_of(u), b.second});
+  }
+  // LPT leaves the makespan up to 4-17 % above the mean when a CTA gets only 3-7 units (batch 4-8: 122 vs a mean
+  // of 116.8 source rows at batch 8; the optimum, found by an integer program over the three unit sizes, is 118).
+  // Local search on the most loaded CTA -- move one of its units, or swap one against a cheaper unit of another
+  // CTA, whichever lowers max(load_a, load_b) most -- reaches that optimum in a few hundred steps.
+  const char *ls_env = getenv("B200CORR_BWD_PLAN_LS");   // diagnostics: 0 = plain LPT
+  if (!ls_env || atoi(ls_env) != 0) {
+    std::vector<long long> load(grid, 0);
+    for (int c = 0; c < grid; ++c)
+      for (int u : lists[c]) load[c] += cost_of(u);
+    for (int iter = 0; iter < 4 * grid + 64; ++iter) {
+      int a = 0;
+      for (int c = 1; c < grid; ++c)
+        if (load[c] > load[a]) a = c;
+      long long best = load[a];
+      int best_b = -1, best_i = -1, best_j = -1;   // j < 0: move lists[a][i] to b; else swap with lists[b][j]
+      for (int b = 0; b < grid; ++b) {
+        if (b == a) continue;
+        int seen_x = -1;
+        for (size_t i = 0; i < lists[a].size(); ++i) {
+          const int x = cost_of(lists[a][i]);
+          if (x == seen_x) continue;              // lists are sorted by cost at first; a repeat changes nothing
+          seen_x = x;
+          const long long mv = std::max(load[a] - x, load[b] + x);
+          if (mv < best) { best = mv; best_b = b; best_i = (int)i; best_j = -1; }
+          int seen_y = -1;
+          for (size_t j = 0; j < lists[b].size(); ++j) {
+            const int y = cost_of(lists[b][j]);
+            if (y >= x || y == seen_y) continue;
+            seen_y = y;
+            const long long sw = std::max(load[a] - x + y, load[b] + x - y);
+            if (sw < best) { best = sw; best_b = b; best_i = (int)i; best_j = (int)j; }
+          }
+        }
+      }
+      if (best_b < 0) break;
+      const int u = lists[a][best_i], x = cost_of(u);
+      if (best_j < 0) {
+        lists[a].erase(lists[a].begin() + best_i);
+        lists[best_b].push_back(u);
+        load[a] -= x; load[best_b] += x;
+      } else {
+        const int v = lists[best_b][best_j], y = cost_of(v);
+        lists[a][best_i] = v; lists[best_b][best_j] = u;
+        load[a] += y - x; load[best_b] += x - y;
+      }
+    }
+    // long units first inside a CTA (what LPT produced, restored after the exchanges): the ring keeps running
+    // across units, so the order only decides which unit is in flight when the kernel drains
+    for (int c = 0; c < grid; ++c)
+      std::stable_sort(lists[c].begin(), lists[c].end(), [&](int a2, int b2) { return cost_of(a2) > cost_of(b2); });
   }
   int off = 0;
   int *ids = h_plan + grid + 1;
