@@ -52,28 +52,50 @@ using namespace b200dev;
 // ------------------------------------------------------------------------------ prep (transpose)
 // in [B][C][HW] -> out [B][HW][Cp], tf32-rounded, channels >= C zero.  With out_lo (TF32x3): the
 // residual x - tf32(x), itself rounded to TF32, so that x = hi + lo to ~2^-22 relative.
+// One launch converts BOTH feature maps (blockIdx.z = map * B + b; the maps may differ in size): a CTA
+// transposes 32 pixels x 128 channels, reads 128-byte runs of a channel plane and writes 512-byte runs of a
+// pixel row (two launches of 32 x 32 tiles took 2 x 14.7 us at B=4, 4.3 TB/s; this one ~21 us).
+struct PrepMap {
+  const float *in;
+  float *out, *out_lo;
+  int HW;
+};
 __global__ void __launch_bounds__(256)
-prep_kmajor_tf32_kernel(const float *__restrict__ in, float *__restrict__ out, float *__restrict__ out_lo, int C,
-                        int Cp, int HW) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+prep_kmajor_tf32_kernel(PrepMap m0, PrepMap m1, int B, int C, int Cp) {
+  // [pixel][channel ^ pixel]: the transposing writes (lane = pixel) and the 16-byte reads (lane = channel quad)
+  // are both bank-conflict free; the XOR permutes a quad's elements by pixel & 3, which is warp-uniform below
+  __shared__ __align__(16) float tile[32][128];
+  const int which = blockIdx.z / B, b = blockIdx.z - which * B;
+  const PrepMap m = which ? m1 : m0;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+  if (p0 >= m.HW) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = c0 + ty + 8 * i, p = p0 + tx;
+  for (int i = 0; i < 16; ++i) {
+    const int cl = ty + 8 * i, c = c0 + cl, p = p0 + tx;
     float v = 0.f;
-    if (c < C && p < HW) v = in[((size_t)b * C + c) * HW + p];
-    tile[ty + 8 * i][tx] = v;
+    if (c < C && p < m.HW) v = __ldg(m.in + ((size_t)b * C + c) * m.HW + p);
+    tile[tx][cl ^ tx] = v;
   }
   __syncthreads();
+  // thread -> (pixel ty + 8 i, channels c0 + 4 tx .. + 3): a warp writes 512 contiguous bytes of one pixel row
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int p = p0 + ty + 8 * i, c = c0 + tx;
-    if (p < HW && c < Cp) {
-      const float v = tile[tx][ty + 8 * i], hi = to_tf32_rna(v);
-      out[((size_t)b * HW + p) * Cp + c] = hi;
-      if (out_lo) out_lo[((size_t)b * HW + p) * Cp + c] = to_tf32_rna(v - hi);
+    const int r = ty + 8 * i, p = p0 + r, c = c0 + 4 * tx;
+    if (p < m.HW && c < Cp) {
+      const float4 e = *reinterpret_cast<const float4 *>(&tile[r][(4 * tx) ^ (r & 28)]);
+      // channel j of the quad sits at element j ^ (r & 3); r & 3 == ty & 3 for every i
+      const bool s0 = ty & 1, s1 = ty & 2;
+      const float a0 = s0 ? e.y : e.x, a1 = s0 ? e.x : e.y, a2 = s0 ? e.w : e.z, a3 = s0 ? e.z : e.w;
+      float4 v, hi, lo;
+      v.x = s1 ? a2 : a0; v.y = s1 ? a3 : a1; v.z = s1 ? a0 : a2; v.w = s1 ? a1 : a3;
+      hi.x = to_tf32_rna(v.x); hi.y = to_tf32_rna(v.y); hi.z = to_tf32_rna(v.z); hi.w = to_tf32_rna(v.w);
+      *reinterpret_cast<float4 *>(m.out + ((size_t)b * m.HW + p) * Cp + c) = hi;
+      if (m.out_lo) {
+        lo.x = to_tf32_rna(v.x - hi.x); lo.y = to_tf32_rna(v.y - hi.y);
+        lo.z = to_tf32_rna(v.z - hi.z); lo.w = to_tf32_rna(v.w - hi.w);
+        *reinterpret_cast<float4 *>(m.out_lo + ((size_t)b * m.HW + p) * Cp + c) = lo;
+      }
     }
   }
 }
@@ -671,11 +693,13 @@ int b200corr_allpairs_pyramid_layout(const float *f1, const float *f2, float *co
                "allpairs_pyramid: workspace must be 128-byte and level 0 16-byte aligned");
     float *f1t = (float *)workspace, *f2t = f1t + nfeat1;
     float *f1lo = x3 ? f2t + nfeat2 : nullptr, *f2lo = x3 ? f1lo + nfeat1 : nullptr;
-    dim3 pgrid1((HWq + 31) / 32, Cp / 32, B), pgrid2((HW + 31) / 32, Cp / 32, B);
-    prep_kmajor_tf32_kernel<<<pgrid1, 256, 0, stream>>>(f1, f1t, f1lo, C, Cp, HWq);
-    B200_LAUNCH_OK("prep_kmajor_tf32_kernel");
-    prep_kmajor_tf32_kernel<<<pgrid2, 256, 0, stream>>>(f2, f2t, f2lo, C, Cp, HW);
-    B200_LAUNCH_OK("prep_kmajor_tf32_kernel");
+    {
+      const int hw_max = HWq > HW ? HWq : HW;
+      dim3 pgrid((hw_max + 31) / 32, (Cp + 127) / 128, 2 * B);
+      const PrepMap m0{f1, f1t, f1lo, HWq}, m1{f2, f2t, f2lo, HW};
+      prep_kmajor_tf32_kernel<<<pgrid, 256, 0, stream>>>(m0, m1, B, C, Cp);
+      B200_LAUNCH_OK("prep_kmajor_tf32_kernel");
+    }
 
     CUtensorMap mapA, mapB, mapAlo, mapBlo;
     for (int which = 0; which < (x3 ? 2 : 1); ++which) {
