@@ -200,6 +200,20 @@ int b200corr_lookup_forward_layout(const float *const *h_levels, int num_levels,
                                    const float *coords, float *out, int B, int H, int W, int radius, int mode,
                                    void *stream);
 
+/* fp16 storage of the blocked levels (opt-in; no counterpart in the reference, whose volume is fp32).  Bit l of
+ * `half_levels` = level l holds fp16 values in the same tile order (a tile is 64 halves = 128 B, offsets and slice
+ * sizes above count elements); half_levels must be 0 or equal to blocked_levels, h_levels[l] of such a level points
+ * to the fp16 buffer.  Each value is rounded once from the fp32 accumulator / the fp32 2x2 mean (round to nearest,
+ * relative 2^-11 -- the size of the TF32 input rounding; finite values beyond +-65504 saturate); the coarse levels
+ * stay fp32.  Halves what the build writes and what the lookups read of the two levels that hold 94 % of the volume. */
+int b200corr_allpairs_pyramid_storage(const float *f1, const float *f2, float *const *h_levels,
+                                      int num_levels, int B, int C, int H1, int W1, int H2, int W2, float scale,
+                                      int precision, int blocked_levels, int half_levels, void *workspace,
+                                      size_t workspace_bytes, void *stream);
+int b200corr_lookup_forward_storage(const float *const *h_levels, int num_levels, int first_level, int blocked_levels,
+                                    int half_levels, const float *coords, float *out, int B, int H, int W, int radius,
+                                    int mode, void *stream);
+
 /* out[B, num_levels*(2r+1)^2, H, W]; coords[B, 2, H, W] (channel 0 = x).  Channel index
  * l*(2r+1)^2 + i*(2r+1) + j, i = x-offset index, j = y-offset index (corr.py:80-86). */
 int b200corr_lookup_forward(const float *const *h_levels, int num_levels, const float *coords,

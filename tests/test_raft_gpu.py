@@ -462,6 +462,76 @@ def test_blocked_volume_layout_equals_rowmajor(shape, levels, precision, expect_
             assert torch.equal(a(c), b(c))
 
 
+@pytest.mark.parametrize("shape,levels,precision", [
+    ((1, 32, 16, 32), 4, "tf32"), ((2, 64, 32, 48), 3, "tf32"), ((1, 16, 48, 160), 4, "tf32x3"), ((1, 24, 16, 16), 1, "tf32"),
+    ((1, 16, 68, 120), 4, "tf32"), ((1, 16, 55, 128), 4, "tf32"), ((2, 8, 13, 24), 3, "tf32"), ((3, 8, 24, 40), 4, "tf32x3"),
+    ((1, 16, 32, 32), 5, "tf32")], ids=str)
+def test_fp16_volume_storage(shape, levels, precision):
+    """storage="fp16" (include/b200corr.h, b200corr_allpairs_pyramid_storage): the two blocked levels hold the fp32
+    values rounded ONCE to fp16 (round to nearest: bit-identical to `.half()` of the fp32 kernel's levels), the
+    coarse levels stay fp32, and every lookup is bit-identical to the fp32 lookup of those rounded values -- hence
+    within 2^-11 * max|level| of the fp32-stored block."""
+    from understanding_flow_robustness_b200 import CorrBlock, coords_grid
+    B, C, H, W = shape
+    torch.manual_seed(H * W + C + 1)
+    f1 = torch.randn(B, C, H, W, device="cuda")
+    f2 = torch.randn(B, C, H, W, device="cuda")
+    with torch.no_grad():
+        a = CorrBlock(f1, f2, levels, 4, precision=precision, layout="auto", storage="fp16")
+        ref = CorrBlock(f1, f2, levels, 4, precision=precision, layout="rowmajor")
+        mask = a._blocked
+        assert mask == (1 if levels == 1 else 3)
+        assert [v.dtype for v in a._levels] == [torch.float16 if (mask >> l) & 1 else torch.float32 for l in range(levels)]
+        rounded = CorrBlock(f1, f2, levels, 4, precision=precision, layout="rowmajor")
+        rounded._levels = [v.half().float() if (mask >> l) & 1 else v for l, v in enumerate(ref.get_corr_pyramid())]
+        for l, (la, lr) in enumerate(zip(a.get_corr_pyramid(), rounded._levels)):
+            assert la.dtype == torch.float32 and la.shape == lr.shape and torch.equal(la, lr), l
+        vmax = max(float(v.abs().max()) for v in ref.get_corr_pyramid())
+        for sigma in (0.0, 3.0, 50.0):
+            c = coords_grid(B, H, W, "cuda") + sigma * torch.randn(B, 2, H, W, device="cuda")
+            out = a(c)
+            assert torch.equal(out, rounded(c))
+            assert float((out - ref(c)).abs().max()) <= 2.0 ** -11 * vmax * 1.0001
+        for r in (1, 2, 3):
+            a.radius = rounded.radius = r
+            c = coords_grid(B, H, W, "cuda") + 2.0 * torch.randn(B, 2, H, W, device="cuda")
+            assert torch.equal(a(c), rounded(c))
+
+
+def test_fp16_volume_storage_saturates_and_keeps_gradients():
+    """Finite values beyond the fp16 range saturate at +-65504 (cvt.rn.satfinite), never inf; the backward does not
+    read the forward volume, so gradients are those of the fp32-stored block; lookup_convc1 still works."""
+    from understanding_flow_robustness_b200 import CorrBlock, coords_grid
+    torch.manual_seed(3)
+    B, C, H, W = 1, 32, 16, 32
+    f1 = torch.randn(B, C, H, W, device="cuda")
+    f2 = torch.randn(B, C, H, W, device="cuda")
+    with torch.no_grad():
+        big = CorrBlock(3000.0 * f1, 3000.0 * f2, 4, 4, precision="tf32", storage="fp16")
+        l0 = big.get_corr_pyramid()[0]
+        assert torch.isfinite(l0).all() and float(l0.abs().max()) == 65504.0
+    c = coords_grid(B, H, W, "cuda") + 2.0 * torch.randn(B, 2, H, W, device="cuda")
+    g = torch.randn(B, 4 * 81, H, W, device="cuda")
+    grads = []
+    for storage in ("fp16", "fp32"):
+        a1, a2 = f1.clone().requires_grad_(), f2.clone().requires_grad_()
+        blk = CorrBlock(a1, a2, 4, 4, precision="tf32", backward_precision="fp32", storage=storage)
+        out = blk(c)
+        grads.append(torch.autograd.grad(out, (a1, a2), g))
+    for x, y in zip(*grads):
+        assert torch.equal(x, y)
+    with torch.no_grad():
+        w = torch.randn(64, 4 * 81, 1, 1, device="cuda")
+        bias = torch.randn(64, device="cuda")
+        blk = CorrBlock(f1, f2, 4, 4, precision="tf32", storage="fp16")
+        want = torch.relu(torch.nn.functional.conv2d(blk(c), w, bias))
+        for impl in ("pipelined", "fused"):
+            got = blk.lookup_convc1(c, w, bias, impl=impl)
+            assert float((got - want).abs().max()) <= 2e-2 * float(want.abs().max())
+    with pytest.raises(ValueError):
+        CorrBlock(f1, f2, 4, 4, layout="rowmajor", storage="fp16")
+
+
 def test_blocked_layout_with_autograd():
     """The backward never reads the forward volume: gradients are those of the row-major block."""
     from understanding_flow_robustness_b200 import CorrBlock, coords_grid

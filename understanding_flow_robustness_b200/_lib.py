@@ -42,6 +42,11 @@ PROTOTYPES = {
                                                  c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200corr_lookup_forward_layout": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                                c_int, c_int, c_int, c_int, c_void_p]),
+    "b200corr_allpairs_pyramid_storage": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int,
+                                                  c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_size_t,
+                                                  c_void_p]),
+    "b200corr_lookup_forward_storage": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                                c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200corr_lookup_forward": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_int,
                                         c_int, c_int, c_int, c_void_p]),
     "b200corr_lookup_forward_from": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p, c_int, c_int,

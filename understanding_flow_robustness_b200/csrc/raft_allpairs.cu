@@ -44,6 +44,8 @@
 //     |vol - exact| <= (2^-10 + 2^-22) * scale * sum_c |f1_c * f2_c|  (+ fp32 accumulation error).
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "tcgen05.cuh"
 
 namespace {
@@ -136,6 +138,13 @@ struct Params {
 };
 }  // namespace tc
 
+// two floats -> packed fp16 pair (lo in the low half), round to nearest, finite values saturate at +-65504
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 // N consecutive floats starting at column x of a row of width WL
 template <int N>
 __device__ __forceinline__ void store_row_vec(float *dst, const float (&v)[N], int x, int WL,
@@ -175,7 +184,11 @@ __device__ __forceinline__ void store_rows_coalesced(float *stage, const float (
 // the accumulator columns of one epilogue step (32 of them) are one half tile (4 rows x 8 columns): still one
 // 128-byte line per query row and store, but the lines of a query's patch are 1 KB contiguous, and the lookup's
 // 10-row windows touch 4-6 tiles of 256 B instead of 10 rows 640 B apart.
-template <int CTAS, bool BLK = false>
+// HALF (BLK only): the two blocked levels are stored as fp16 (8x8 tiles of 64 halves = 128 B): half the volume bytes
+// for the build to write and the lookups to read.  The values are rounded once, from the fp32 accumulator / the fp32
+// 2x2 mean (cvt.rn.satfinite: relative 2^-11, the size of the TF32 input rounding; |v| > 65504 saturates); levels 2-3
+// stay fp32.  Staging rows shrink to 64 B (level 0) and 32 B (level 1): half the shared-memory round trip as well.
+template <int CTAS, bool BLK = false, bool HALF = false>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapBlo,
@@ -356,13 +369,37 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         for (int i = 0; i < 32; ++i) cur[i] *= p.scale;
         // ---- level 0: one patch row of 32 query rows -> swizzled staging -> full-line streaming stores
         __syncwarp();   // previous readers of the staging tile are done
+        if constexpr (HALF) {
+          // half a tile = 32 halves = 64 B per query row: staged like level 1 of the fp32 kernel
+          uint32_t h[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) h[i] = pack_half2_sat(cur[2 * i], cur[2 * i + 1]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4 *>(ebuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+          __syncwarp();
+          if (!(p.debug & 1)) {
+            const size_t toff = ((size_t)(y0 >> 3) * p.TW0 + (x0 >> 3) + r) * 64 + half * 32 + 8 * xchunk;   // halves
+            __half *vol0h = reinterpret_cast<__half *>(vol0);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int row = it * 8 + xrow;
+              const uint4 v = *reinterpret_cast<const uint4 *>(ebuf + row * 64 + ((xchunk ^ ((row >> 1) & 3)) << 4));
+              const int mm = mrow0 + row;
+              if (mm < p.HW && x0 + 8 * r < p.W)
+                __stcs(reinterpret_cast<uint4 *>(vol0h + ((size_t)bst * p.HW + mm) * (size_t)p.S0 + toff), v);
+            }
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int off = lane * 128 + ((j ^ (lane & 7)) << 4);
           *reinterpret_cast<float4 *>(ebuf + off) = make_float4(cur[4 * j], cur[4 * j + 1], cur[4 * j + 2], cur[4 * j + 3]);
         }
         __syncwarp();
-        if (!(p.debug & 1)) {
+        }
+        if (!HALF && !(p.debug & 1)) {
           if constexpr (BLK) {
             // cur = tile column r of this half: rows 4*half..4*half+3 x columns x0+8r..x0+8r+7 = half a tile
             const size_t toff = ((size_t)(y0 >> 3) * p.TW0 + (x0 >> 3) + r) * 64 + half * 32 + 4 * wchunk;
@@ -406,7 +443,30 @@ allpairs_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 p1[yy * 8 + xx] = prev[yy * 4 + xx];
                 p1[yy * 8 + 4 + xx] = p1h[yy * 4 + xx];
               }
-            if (p.lvl[0] && m_dbg) {
+            if (HALF && p.lvl[0] && m_dbg) {
+              // [2 rows][8 columns] = 16 halves = one 32-byte sector of a level-1 tile per query row
+              const int y1 = y0 / 2 + 2 * half;
+              const size_t toff = ((size_t)(y1 >> 3) * p.TW1 + (x0 >> 4) + (r >> 1)) * 64 + (y1 & 7) * 8;   // halves
+              uint32_t h1[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h1[i] = pack_half2_sat(p1[2 * i], p1[2 * i + 1]);
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<uint4 *>(ebuf + lane * 32 + ((j ^ ((lane >> 2) & 1)) << 4)) =
+                    make_uint4(h1[4 * j], h1[4 * j + 1], h1[4 * j + 2], h1[4 * j + 3]);
+              __syncwarp();
+              __half *l1h = reinterpret_cast<__half *>(p.lvl[0]);
+#pragma unroll
+              for (int it = 0; it < 2; ++it) {
+                const int row = it * 16 + (lane >> 1), ch = lane & 1;
+                const uint4 v = *reinterpret_cast<const uint4 *>(ebuf + row * 32 + ((ch ^ ((row >> 2) & 1)) << 4));
+                const int mm = mrow0 + row;
+                if (mm < p.HW && x0 / 2 + 8 * (r >> 1) < p.LW[0])
+                  __stcs(reinterpret_cast<uint4 *>(l1h + ((size_t)bst * p.HW + mm) * (size_t)p.S1 + toff + 8 * ch), v);
+              }
+            }
+            if (!HALF && p.lvl[0] && m_dbg) {
               const int y1 = y0 / 2 + 2 * half;                    // first of the two level-1 rows
               const size_t toff = ((size_t)(y1 >> 3) * p.TW1 + (x0 >> 4) + (r >> 1)) * 64 + (y1 & 7) * 8 + 4 * xchunk;
               const size_t slice = (size_t)p.S1;
@@ -648,7 +708,18 @@ int b200corr_allpairs_pyramid_layout(const float *f1, const float *f2, float *co
                                      int num_levels, int B, int C, int H1, int W1, int H, int W, float scale,
                                      int precision, int blocked_levels, void *workspace, size_t workspace_bytes,
                                      void *stream_) {
+  return b200corr_allpairs_pyramid_storage(f1, f2, h_levels, num_levels, B, C, H1, W1, H, W, scale, precision,
+                                           blocked_levels, 0, workspace, workspace_bytes, stream_);
+}
+
+int b200corr_allpairs_pyramid_storage(const float *f1, const float *f2, float *const *h_levels,
+                                      int num_levels, int B, int C, int H1, int W1, int H, int W, float scale,
+                                      int precision, int blocked_levels, int half_levels, void *workspace,
+                                      size_t workspace_bytes, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK(half_levels == 0 || (blocked_levels != 0 && half_levels == blocked_levels),
+             "allpairs_pyramid: fp16 storage covers exactly the blocked levels (half_levels %d, blocked_levels %d)",
+             half_levels, blocked_levels);
   B200_CHECK(blocked_levels == 0 || blocked_levels == b200corr_allpairs_blocked_levels(num_levels, H, W, precision),
              "allpairs_pyramid: blocked_levels %d not available for this problem (ask b200corr_allpairs_blocked_levels)",
              blocked_levels);
@@ -773,7 +844,11 @@ int b200corr_allpairs_pyramid_layout(const float *f1, const float *f2, float *co
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      if (blocked_levels) {
+      if (blocked_levels && half_levels) {
+        static bool attr_blkh[64] = {};
+        if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel<2, true, true>, tc::Cfg<2>::SMEM_BYTES, attr_blkh)) return e;
+        B200_CUDA(cudaLaunchKernelEx(&cfg, allpairs_tc_kernel<2, true, true>, mapA, mapB, mapAlo, mapBlo, p));
+      } else if (blocked_levels) {
         static bool attr_blk[64] = {};
         if (int e = b200::set_max_smem_once((const void *)allpairs_tc_kernel<2, true>, tc::Cfg<2>::SMEM_BYTES, attr_blk)) return e;
         B200_CUDA(cudaLaunchKernelEx(&cfg, allpairs_tc_kernel<2, true>, mapA, mapB, mapAlo, mapBlo, p));

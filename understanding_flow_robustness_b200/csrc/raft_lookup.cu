@@ -73,13 +73,17 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
   // staged column of window column 0, and the staged columns the taps touch
   const int shift = path == PATH_SCALAR ? 0 : (a.ox & 3);
   a.clo = shift + xlo; a.chi = shift + xhi;
-  a.slice = p.lvl[lvl] + ((size_t)b * p.HW + (a.q_ok ? q : 0)) * (size_t)p.slice[lvl];
   a.blocked = p.blocked[lvl] != 0;
+  {
+    const size_t e0 = ((size_t)b * p.HW + (a.q_ok ? q : 0)) * (size_t)p.slice[lvl];   // in elements
+    a.slice = path == PATH_HALF ? reinterpret_cast<const float *>(reinterpret_cast<const __half *>(p.lvl[lvl]) + e0) : p.lvl[lvl] + e0;
+  }
   a.tiles_w = p.tiles_w[lvl];
 
   // ---- this warp's window rows: all loads in flight together, parked in the tile after the tap tables
   float sv[RPW][24];
   if (path == PATH_SECTOR) stage_load<PATH_SECTOR, RPW, WS>(a, warp * RPW, sv);
+  else if (path == PATH_HALF) stage_load_half<WS, RPW>(a, warp, sv);
   else if (path == PATH_VEC4) stage_load<PATH_VEC4, RPW, WS>(a, warp * RPW, sv);
   else stage_load<PATH_SCALAR, RPW, WS>(a, warp * RPW, sv);
   // ---- this warp's share of the 2N tap table entries
@@ -98,6 +102,7 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
     tab_a[e][lane] = frac;
   }
   if (path == PATH_SECTOR) stage_store<PATH_SECTOR, RPW, WS>(win, lane, a, warp * RPW, sv);
+  else if (path == PATH_HALF) stage_store_half<WS, RPW>(win, lane, a, warp, sv);
   else if (path == PATH_VEC4) stage_store<PATH_VEC4, RPW, WS>(win, lane, a, warp * RPW, sv);
   else stage_store<PATH_SCALAR, RPW, WS>(win, lane, a, warp * RPW, sv);
   __syncthreads();
@@ -495,7 +500,16 @@ int b200corr_lookup_forward_from(const float *const *h_levels, int num_levels, i
 int b200corr_lookup_forward_layout(const float *const *h_levels, int num_levels, int first_level, int blocked_levels,
                                    const float *coords, float *out, int B, int H, int W, int radius, int mode,
                                    void *stream_) {
+  return b200corr_lookup_forward_storage(h_levels, num_levels, first_level, blocked_levels, 0, coords, out, B, H, W,
+                                         radius, mode, stream_);
+}
+
+int b200corr_lookup_forward_storage(const float *const *h_levels, int num_levels, int first_level, int blocked_levels,
+                                    int half_levels, const float *coords, float *out, int B, int H, int W, int radius,
+                                    int mode, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK((half_levels & ~blocked_levels) == 0, "lookup_forward: only blocked levels can be stored in fp16 (half_levels %d, blocked_levels %d)",
+             half_levels, blocked_levels);
   LookupParams p;
   if (B == 0) return 0;   // empty tensors have no storage: nothing to validate, nothing to do
   if (int e = fill_params(p, h_levels, nullptr, num_levels, B, H, W, radius, mode, "lookup_forward", first_level)) return e;
@@ -510,7 +524,8 @@ int b200corr_lookup_forward_layout(const float *const *h_levels, int num_levels,
                  "lookup_forward: level %d (%dx%d) cannot be in the blocked layout", l, p.LH[l], p.LW[l]);
       int hp, wp;
       b200corr_blocked_level_dims(l, H, W, &hp, &wp);
-      p.blocked[l] = 1; p.path[l] = PATH_SECTOR; p.tiles_w[l] = wp / 8; p.slice[l] = (long long)hp * wp;
+      const bool hl = (half_levels >> l) & 1;
+      p.blocked[l] = hl ? 2 : 1; p.path[l] = hl ? PATH_HALF : PATH_SECTOR; p.tiles_w[l] = wp / 8; p.slice[l] = (long long)hp * wp;
     }
   }
   B200_CHECK((blocked_levels >> num_levels) == 0, "lookup_forward: blocked_levels names a level that is not there");

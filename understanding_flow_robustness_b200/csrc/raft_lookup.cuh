@@ -2,6 +2,7 @@
 // lookup_convc1.cu (the lookup fused with the motion encoder's 1x1 convolution): level parameters, the
 // coordinate arithmetic of grid_sample reproduced operation by operation, and the window staging.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace b200lookup {
@@ -15,7 +16,7 @@ struct LookupParams {
   int LH[kMaxLevels], LW[kMaxLevels];
   int path[kMaxLevels];  // access flavour per level (sector / 16-byte / scalar), from width and alignment
   int num_levels, B, HW, radius, mode;
-  int blocked[kMaxLevels];   // forward only: the level is stored as 8x8 tiles of 64 floats (b200corr.h)
+  int blocked[kMaxLevels];   // forward only: 1 = the level is stored as 8x8 tiles of 64 floats (b200corr.h), 2 = as 8x8 tiles of 64 fp16 values
   int tiles_w[kMaxLevels];   // blocked levels: tiles per row of the padded slice
   long long slice[kMaxLevels];   // floats per query slice (LH * LW, or the padded size of a blocked level)
   int first_level;   // pyramid level of list entry 0: entry i has extent (H, W) >> (first_level + i), coordinate scale 2^-(first_level + i)
@@ -107,7 +108,7 @@ __device__ __forceinline__ int window_origin(float c, int lvl, int &lo, int &hi)
 }
 
 constexpr int kCols = 16;  // staged columns per window row: (ox & 3) + 2r + 4 <= 15 for r <= 4
-enum { PATH_SCALAR = 0, PATH_VEC4 = 1, PATH_SECTOR = 2 };
+enum { PATH_SCALAR = 0, PATH_VEC4 = 1, PATH_SECTOR = 2, PATH_HALF = 3 };   // PATH_HALF: blocked fp16 tiles, column geometry of PATH_SECTOR
 
 struct StageArgs {
   const float *slice;  // this lane's H_l x W_l slice
@@ -115,7 +116,7 @@ struct StageArgs {
   int ylo, yhi;        // window rows the taps touch
   int clo, chi;        // staged columns the taps touch
   bool q_ok;
-  bool blocked;        // PATH_SECTOR only: the slice is a grid of 8x8 tiles (64 consecutive floats each)
+  bool blocked;        // PATH_SECTOR / PATH_HALF: the slice is a grid of 8x8 tiles (64 consecutive values each)
   int tiles_w;         // tiles per row of a blocked slice
 };
 
@@ -179,6 +180,70 @@ __device__ __forceinline__ void stage_store(float *win, int lane, const StageArg
   }
 }
 
+
+// ---- PATH_HALF: blocked fp16 tiles (a.slice addresses halves; the slice sizes count elements).  A 32-byte sector of
+// such a tile holds TWO rows (y even, y + 1) of 8 columns, so the window is fetched by aligned row PAIRS: 5-6 pairs
+// x 2-3 tile columns = ~12 sector loads per window instead of ~21.  Pair j of the window starts at row
+// (oy & ~1) + 2 j, j = 0..6; warp w fetches pairs w and w + 4.  hv[jj][8 g + 4 rr + e]: packed halves 2e, 2e+1 of
+// row rr of tile column g; everything stays packed until stage_store_half, so all loads of a warp are in flight
+// together (a conversion right behind each load serialised them: 48.6 instead of 29.4 us per lookup).
+template <int WS, int NR>
+__device__ __forceinline__ void stage_load_half(const StageArgs &a, int warp, float (&hv)[NR][24]) {
+  static_assert(NR >= 2 && WS / 2 + 1 <= 8, "two row pairs per warp cover the window");
+  const int c0 = a.ox & ~7, ybase = a.oy & ~1;
+  const bool hi4 = (a.ox & 4) != 0;
+  const int llo = hi4 ? a.clo + 4 : a.clo, lhi = hi4 ? a.chi + 4 : a.chi;
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    const int y0 = ybase + 2 * (warp + 4 * jj);
+#pragma unroll
+    for (int k = 0; k < 24; ++k) hv[jj][k] = 0.f;
+    bool need = false;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int y = y0 + rr, wr = y - a.oy;
+      need = need || (wr >= a.ylo && wr <= a.yhi && wr < WS && y >= 0 && y < a.LH);
+    }
+    need = need && a.q_ok;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      const int x = c0 + 8 * g;
+      if (need && x >= 0 && x < a.LW && lhi >= 8 * g && llo < 8 * g + 8) {
+        const __half *hp = reinterpret_cast<const __half *>(a.slice) +
+                           ((size_t)((y0 >> 3) * a.tiles_w + (x >> 3)) * 64 + (y0 & 7) * 8);
+        ldg256(reinterpret_cast<const float *>(hp), *reinterpret_cast<float(*)[8]>(&hv[jj][8 * g]));
+      }
+    }
+  }
+}
+
+template <int WS, int NR>
+__device__ __forceinline__ void stage_store_half(float *win, int lane, const StageArgs &a, int warp, const float (&hv)[NR][24]) {
+  const bool hi4 = (a.ox & 4) != 0;
+  const int ybase = a.oy & ~1;
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int y = ybase + 2 * (warp + 4 * jj) + rr, wr = y - a.oy;
+      if (wr < 0 || wr >= WS) continue;
+      // rows the taps do not touch / outside the level are staged as zero (the tile rows past the extent of a
+      // padded level are not zero in memory)
+      const bool row_ok = a.q_ok && wr >= a.ylo && wr <= a.yhi && y >= 0 && y < a.LH;
+      float *dst = win + (wr * kCols) * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        // loaded column idx = k (+ 4 when the window starts in the upper half of a tile row): half idx & 1 of
+        // register 8 (idx >> 3) + 4 rr + ((idx & 7) >> 1); idx and idx + 4 share the half position
+        const float ra = hv[jj][8 * (k >> 3) + 4 * rr + ((k & 7) >> 1)];
+        const float rb = hv[jj][8 * ((k + 4) >> 3) + 4 * rr + (((k + 4) & 7) >> 1)];
+        const __half2 h2 = *reinterpret_cast<const __half2 *>(hi4 ? &rb : &ra);
+        const float f = (k & 1) ? __high2float(h2) : __low2float(h2);
+        dst[k * 32] = row_ok ? f : 0.f;
+      }
+    }
+  }
+}
 
 inline int fill_params(LookupParams &p, const float *const *lv, float *const *glv, int num_levels, int B,
                 int H, int W, int radius, int mode, const char *who, int first_level = 0) {

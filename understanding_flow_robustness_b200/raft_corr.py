@@ -78,13 +78,20 @@ def _level_shapes(H, W, num_levels):
 
 # ------------------------------------------------------------------------------------------------
 # raw C-ABI calls
-def allpairs_pyramid(fmap1, fmap2, num_levels=4, precision="tf32", blocked=False):
+def allpairs_pyramid(fmap1, fmap2, num_levels=4, precision="tf32", blocked=False, storage="fp32"):
     """List of (B*H*W, 1, H_l, W_l) tensors: vol_0 = f1^T f2 / sqrt(C), vol_{l+1} = avg_pool2d(vol_l, 2, 2).
 
     blocked=True returns `(levels, mask)`: the levels whose bit is set in `mask` hold each slice as a grid of 8x8
     tiles of 64 consecutive floats (include/b200corr.h, "blocked volume layout") -- same tensor shapes, same
     values, another element order; `deblock()` gives the reference's row-major view of such a level.  mask is 0
-    where the library has no blocked kernel for the problem."""
+    where the library has no blocked kernel for the problem.
+    storage="fp16" (with blocked=True): the blocked levels are fp16 tensors (include/b200corr.h,
+    b200corr_allpairs_pyramid_storage) -- half the bytes to write and to look up; returns `(levels, mask)` where the
+    levels in `mask` have dtype float16.  Falls back to fp32 storage where there is no blocked kernel (mask 0)."""
+    if storage not in ("fp32", "fp16"):
+        raise ValueError("allpairs_pyramid: storage must be 'fp32' or 'fp16'")
+    if storage == "fp16" and not blocked:
+        raise ValueError("allpairs_pyramid: fp16 storage exists for the blocked layout only (blocked=True)")
     fmap1 = fmap1.contiguous()
     fmap2 = fmap2.contiguous()
     _require_cuda_f32("allpairs_pyramid", fmap1, fmap2)
@@ -99,14 +106,16 @@ def allpairs_pyramid(fmap1, fmap2, num_levels=4, precision="tf32", blocked=False
     for l in range(num_levels):
         if (mask >> l) & 1:
             shapes[l] = blocked_level_dims(l, H, W)   # padded to whole 8x8 tiles
-    levels = [torch.empty((B * H * W, 1, h, w), dtype=torch.float32, device=fmap1.device) for (h, w) in shapes]
+    half_mask = mask if storage == "fp16" else 0
+    levels = [torch.empty((B * H * W, 1, h, w), dtype=torch.float16 if (half_mask >> l) & 1 else torch.float32,
+                          device=fmap1.device) for l, (h, w) in enumerate(shapes)]
     nbytes = L.b200corr_allpairs_workspace_bytes(B, C, H, W, prec)
     ws = torch.empty((max(nbytes, 1) + 127) // 128 * 32, dtype=torch.float32, device=fmap1.device)
     with torch.cuda.device(fmap1.device):
-        code = L.b200corr_allpairs_pyramid_layout(_lib.ptr(fmap1), _lib.ptr(fmap2), _lib.ptr_array(levels), num_levels,
-                                                  B, C, H, W, H, W, 1.0 / math.sqrt(C), prec, mask, _lib.ptr(ws), nbytes,
-                                                  _lib.current_stream(fmap1.device))
-    _lib.check(code, "b200corr_allpairs_pyramid_layout")
+        code = L.b200corr_allpairs_pyramid_storage(_lib.ptr(fmap1), _lib.ptr(fmap2), _lib.ptr_array(levels), num_levels,
+                                                   B, C, H, W, H, W, 1.0 / math.sqrt(C), prec, mask, half_mask,
+                                                   _lib.ptr(ws), nbytes, _lib.current_stream(fmap1.device))
+    _lib.check(code, "b200corr_allpairs_pyramid_storage")
     return (levels, mask) if blocked else levels
 
 
@@ -121,22 +130,38 @@ def deblock(level, h, w):
     """Row-major (Q, 1, h, w) copy of a level stored in the blocked layout (padded to (Hp, Wp) = level.shape[2:])."""
     Q, _, hp, wp = level.shape
     full = level.view(Q, hp // 8, wp // 8, 8, 8).permute(0, 1, 3, 2, 4).reshape(Q, 1, hp, wp)
-    return full[:, :, :h, :w].contiguous()
+    return full[:, :, :h, :w].float().contiguous()    # fp16-stored levels come back as fp32 (exact)
+
+
+def _half_mask(levels, blocked_levels):
+    """Bit i: levels[i] is an fp16 tensor (legal for blocked levels only)."""
+    m = 0
+    for i, v in enumerate(levels):
+        if v.dtype == torch.float16:
+            if not (blocked_levels >> i) & 1:
+                raise RuntimeError("lookup: an fp16 level must be in the blocked layout")
+            m |= 1 << i
+    return m
 
 
 def lookup_forward(levels, coords, radius, H, W, mode="grid_sample", first_level=0, blocked_levels=0):
     """`levels[i]` is pyramid level first_level + i: extent (H, W) >> (first_level + i), sampled at
-    coords / 2^(first_level + i).  Bit i of `blocked_levels`: levels[i] is in the blocked layout."""
+    coords / 2^(first_level + i).  Bit i of `blocked_levels`: levels[i] is in the blocked layout; a blocked level
+    may be an fp16 tensor (allpairs_pyramid(..., storage="fp16"))."""
     coords = coords.contiguous()
-    _require_cuda_f32("lookup_forward", coords, *levels)
+    half = _half_mask(levels, blocked_levels)
+    _require_cuda_f32("lookup_forward", coords, *[v for i, v in enumerate(levels) if not (half >> i) & 1])
+    for v in levels:
+        if not v.is_cuda or v.device != coords.device:
+            raise RuntimeError("lookup_forward: levels and coords must be CUDA tensors on the same device")
     B = coords.shape[0]
     n = (2 * radius + 1) ** 2
     out = torch.empty((B, len(levels) * n, H, W), dtype=torch.float32, device=coords.device)
     with torch.cuda.device(coords.device):
-        code = _lib.lib().b200corr_lookup_forward_layout(_lib.ptr_array(levels), len(levels), first_level,
-                                                         blocked_levels, _lib.ptr(coords), _lib.ptr(out), B, H, W,
-                                                         radius, LOOKUP_MODES[mode], _lib.current_stream(coords.device))
-    _lib.check(code, "b200corr_lookup_forward_layout")
+        code = _lib.lib().b200corr_lookup_forward_storage(_lib.ptr_array(levels), len(levels), first_level,
+                                                          blocked_levels, half, _lib.ptr(coords), _lib.ptr(out), B, H, W,
+                                                          radius, LOOKUP_MODES[mode], _lib.current_stream(coords.device))
+    _lib.check(code, "b200corr_lookup_forward_storage")
     return out
 
 
@@ -418,7 +443,7 @@ class CorrBlock:
     no gradient; gradients flow through the lookups (`__call__`), whose coordinates are detached as in raft.py:188."""
 
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, compute_spatial=False, precision=None,
-                 lookup_mode="grid_sample", layout="auto", backward_precision=None):
+                 lookup_mode="grid_sample", layout="auto", backward_precision=None, storage=None):
         """precision: "tf32x3" (default: split-TF32 on the tensor cores, the accuracy of the reference's fp32
         matmul), "tf32" (one TF32 pass, half the build time, |err| <= 2^-10 * sum|f1 f2| / sqrt(C)) or "fp32"
         (CUDA cores).  None reads the environment variable B200CORR_VOLUME_PRECISION, so a caller that cannot
@@ -429,7 +454,19 @@ class CorrBlock:
         precision="fp32").  B200CORR_VOLUME_BACKWARD_PRECISION overrides the default.
         layout: "auto" keeps the two fine levels in the blocked layout (8x8 tiles, include/b200corr.h) where the
         library supports the problem -- the lookups read them 1.4x faster; `corr_pyramid` / `get_corr_pyramid()`
-        still hand out the reference's row-major tensors (converted on first use).  "rowmajor": as the reference."""
+        still hand out the reference's row-major tensors (converted on first use).  "rowmajor": as the reference.
+        storage: "fp32" (default) or "fp16" -- the two blocked levels (94 % of the volume) kept as fp16: each value
+        rounded once from the fp32 accumulator (relative 2^-11, the size of the TF32 input rounding; saturates at
+        +-65504), half the bytes for the build to write and every lookup to read, half the memory.  Opt-in (None
+        reads B200CORR_VOLUME_STORAGE); needs layout="auto"; gradients are unaffected (the backward never reads
+        the forward volume)."""
+        if storage is None:
+            storage = os.environ.get("B200CORR_VOLUME_STORAGE", "fp32")
+        if storage not in ("fp32", "fp16"):
+            raise ValueError("CorrBlock: storage must be 'fp32' or 'fp16'")
+        if storage == "fp16" and layout != "auto":
+            raise ValueError("CorrBlock: fp16 storage needs layout='auto' (it exists for the blocked levels)")
+        self.storage = storage
         self.num_levels = num_levels
         self.radius = radius
         self.compute_spatial = compute_spatial
@@ -474,7 +511,8 @@ class CorrBlock:
 
     def _build(self, fmap1, fmap2):
         if self._want_blocked:
-            self._levels, self._blocked = allpairs_pyramid(fmap1, fmap2, self.num_levels, self.precision, blocked=True)
+            self._levels, self._blocked = allpairs_pyramid(fmap1, fmap2, self.num_levels, self.precision, blocked=True,
+                                                           storage=self.storage)
         else:
             self._levels, self._blocked = allpairs_pyramid(fmap1, fmap2, self.num_levels, self.precision), 0
         self._rowmajor = None
@@ -542,6 +580,13 @@ class CorrBlock:
                                       self.lookup_mode, blocked_levels=self._blocked)
                 outs.append(conv1x1_forward(corr, weight, bias, relu))
             return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        if any(v.dtype != torch.float32 for v in self._levels):
+            # the one-kernel variant reads fp32 volumes only: plain lookup (which reads fp16 tiles) + convolution
+            out = conv1x1_forward(self(coords), weight, bias, relu) if nin % 4 == 0 and (self.H * self.W) % 4 == 0 else None
+            if out is None:
+                out = F.conv2d(self(coords), weight.reshape(n_out, -1, 1, 1), bias)
+                out = F.relu(out) if relu else out
+            return out
         wp = prepare_convc1(weight, self.num_levels, self.radius)
         return lookup_convc1_forward(self._levels, coords, wp, bias, n_out, self.radius, self.H, self.W,
                                      self.lookup_mode, self._blocked, relu)
