@@ -90,16 +90,17 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
   const float smx = (float)(a.LW - 1), smy = (float)(a.LH - 1);
   const float ismx = __frcp_rn(smx), ismy = __frcp_rn(smy);
 #pragma unroll 1
-  for (int e = warp; e < 2 * N; e += 4) {
-    const bool isy = e >= N;
-    int rel;
-    float frac;
-    one_tap<R>(isy ? cy : cx, slvl, isy ? e - N : e, isy ? smy : smx, isy ? ismy : ismx, mode, isy ? a.oy : a.ox, rel, frac);
+  for (int t = warp; t < N; t += 4) {
+    int relx, rely;
+    float fracx, fracy;
+    two_taps<R>(cx, cy, slvl, t, smx, smy, ismx, ismy, mode, a.ox, a.oy, relx, fracx, rely, fracy);
     // a tap outside the staged rows / columns cannot happen (window_origin); drop it if it does
-    const int lo = isy ? a.ylo : xlo, hi = isy ? a.yhi : xhi;
-    if (rel >= 0 && (rel < lo || rel + 1 > hi)) { rel = -1; frac = 0.f; }
-    tab_r[e][lane] = rel;
-    tab_a[e][lane] = frac;
+    if (relx >= 0 && (relx < xlo || relx + 1 > xhi)) { relx = -1; fracx = 0.f; }
+    if (rely >= 0 && (rely < a.ylo || rely + 1 > a.yhi)) { rely = -1; fracy = 0.f; }
+    tab_r[t][lane] = relx;
+    tab_a[t][lane] = fracx;
+    tab_r[N + t][lane] = rely;
+    tab_a[N + t][lane] = fracy;
   }
   if (path == PATH_SECTOR) stage_store<PATH_SECTOR, RPW, WS>(win, lane, a, warp * RPW, sv);
   else if (path == PATH_HALF) stage_store_half<WS, RPW>(win, lane, a, warp, sv);

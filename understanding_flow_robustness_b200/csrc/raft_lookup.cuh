@@ -90,6 +90,45 @@ __device__ __forceinline__ void one_tap(float c, int lvl, int t, float sm1, floa
   }
 }
 
+// The x tap and the y tap of index t in one pass: the coordinate arithmetic above on packed fp32 pairs
+// (add / mul / fma .f32x2, sm_100: each half rounded exactly like the scalar instruction, so the values are the
+// scalar routine's bit for bit).  The lookup kernels are bound by instruction issue, not by their gathers (with the
+// window loads switched off a lookup takes the same 31 us), and the tap tables were a quarter of all instructions.
+template <int R>
+__device__ __forceinline__ void two_taps(float cx, float cy, int lvl, int t, float smx, float smy, float ismx, float ismy,
+                                         int mode, int ox, int oy, int &relx, float &fracx, int &rely, float &fracy) {
+  constexpr int WS = 2 * R + 4;
+  const float sc = 1.0f / (float)(1 << lvl), off = (float)(t - R);
+  float2 x = __fadd2_rn(__fmul2_rn(make_float2(cx, cy), make_float2(sc, sc)), make_float2(off, off));
+  if (mode != B200CORR_LOOKUP_DIRECT) {
+    const float2 a = __fmul2_rn(make_float2(2.0f, 2.0f), x);
+    const float2 y = make_float2(ismx, ismy);
+    const float2 q = __fmul2_rn(a, y);
+    const float2 r = __ffma2_rn(q, make_float2(-smx, -smy), a);     // a - b q, exact
+    float2 d = __ffma2_rn(r, y, q);
+    // zero, non-finite and huge operands take the IEEE routine (div_by)
+    if (!(fabsf(a.x) < 1e30f) || !(smx >= 1.f)) d.x = __fdiv_rn(a.x, smx);
+    if (!(fabsf(a.y) < 1e30f) || !(smy >= 1.f)) d.y = __fdiv_rn(a.y, smy);
+    const float2 g = __fadd2_rn(d, make_float2(-1.0f, -1.0f));
+    x = __fmul2_rn(__fmul2_rn(__fadd2_rn(g, make_float2(1.0f, 1.0f)), make_float2(0.5f, 0.5f)), make_float2(smx, smy));
+  }
+  const float fx = floorf(x.x), fy = floorf(x.y);
+  if (fabsf(fx) < 1e8f) {
+    relx = (int)fx - ox;
+    fracx = x.x - fx;
+    if (relx < 0 || relx > WS - 2) { relx = -1; fracx = 0.f; }
+  } else {
+    relx = 0; fracx = x.x - x.x;
+  }
+  if (fabsf(fy) < 1e8f) {
+    rely = (int)fy - oy;
+    fracy = x.y - fy;
+    if (rely < 0 || rely > WS - 2) { rely = -1; fracy = 0.f; }
+  } else {
+    rely = 0; fracy = x.y - x.y;
+  }
+}
+
 // Window origin floor(c / 2^l) - R - 1 from the un-rounded centre, and the window rows/columns
 // [lo, hi] the taps can touch: the coordinate arithmetic (fp32 add, and in grid_sample mode the
 // normalise / un-normalise round trip) moves a sample position by < 1e-3 pixel for |c| < 1024, so
