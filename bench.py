@@ -974,8 +974,26 @@ def raft_bench(dev):
         look_rm_ms = timed(lrm_fn, 5) / c["iters"]
         layout_mask = None
         rm[0] = None
+        # opt-in fp16 storage of the two blocked levels (include/b200corr.h): same metric, half the volume bytes
+        hf = [None]
+
+        def build_hf():
+            hf[0] = None
+            hf[0] = CorrBlock(f1, f2, c["levels"], c["radius"], precision="tf32", storage="fp16")
+
+        def lookups_hf():
+            for cc in coords:
+                hf[0](cc)
+        bhf_fn, _ = graphed(build_hf)
+        build_hf_ms = timed(bhf_fn, 5)
+        build_hf()
+        lhf_fn, _ = graphed(lookups_hf)
+        look_hf_ms = timed(lhf_fn, 5) / c["iters"]
+        hf_bytes = int(sum(v.numel() * v.element_size() for v in hf[0]._levels))
+        hf[0] = None
         build()
         layout_mask = blk[0]._blocked
+        fp32_bytes = int(sum(v.numel() * v.element_size() for v in blk[0]._levels))
         from understanding_flow_robustness_b200 import raft_corr
         alt = AlternateCorrBlock(f1, f2, c["levels"], c["radius"])
         alt_ms = timed(lambda: alt(coords[0]), 3)
@@ -1067,6 +1085,12 @@ def raft_bench(dev):
                                       "corr_pyramid / get_corr_pyramid() convert to the reference's row-major view on demand",
                               "rowmajor_build_ms": build_rm_ms, "rowmajor_lookup_ms": look_rm_ms,
                               "rowmajor_ms_per_iter": (build_rm_ms + c["iters"] * look_rm_ms) / c["iters"]},
+            "fp16_storage": {"build_ms": build_hf_ms, "lookup_ms": look_hf_ms,
+                             "ms_per_iter": (build_hf_ms + c["iters"] * look_hf_ms) / c["iters"],
+                             "volume_bytes": hf_bytes, "volume_bytes_fp32": fp32_bytes,
+                             "what": "CorrBlock(storage='fp16'), opt-in: levels 0-1 (94 % of the volume) stored as fp16 tiles, "
+                                     "each value rounded once from the fp32 accumulator (relative 2^-11, saturating); NOT the "
+                                     "configuration of ms_per_iter / roofline above, which keep the reference's fp32 volume"},
             "alt_corr_ms_per_iter": alt_ms,
             "alt_corr": alt_rows, "lookup_backward_ms": lookup_bwd_ms, "build_tf32x3_ms": build_x3_ms,
             "lookup_convc1": fuse_row,
@@ -1082,9 +1106,10 @@ def raft_bench(dev):
                                 "unit": "GB/s", "frac": look_bytes / (look_ms * 1e-3) / 1e9 / hbm, "peak_source": src,
                                 "bytes": "324-channel output written + 4 levels x 10x10 window read per query",
                                 "traffic": traffic("lookup_fwd_kernel"),
-                                "gather_bound": "scripts/probes/gather_probe2.cu: the window bytes of one lookup alone take 21.3 us "
-                                                "(3.7 TB/s of requested bytes) whatever the request shape; + the result at the copy "
-                                                "peak = 27.4 us (DESIGN.md 2.6)"},
+                                "what_bounds_it": "not the gather: with the window loads switched off the kernel takes the same time, "
+                                                  "and the pieces (CTA prologue 7.4, tap tables 5.2, parking 2.1, loads 6, sampling "
+                                                  "6.6, stores 3.4 us) add up -- a per-CTA latency chain at 4 CTAs per SM "
+                                                  "(DESIGN.md 2.4, 2.6)"},
             "roofline": {"bound": "hbm", "what": "(build + 12 lookups) / 12 against the algorithmic bytes of both at the HBM copy peak",
                          "bound_ms_per_iter": (vol_bytes + c["iters"] * look_bytes) / (hbm * 1e9) * 1e3 / c["iters"],
                          "frac": (vol_bytes + c["iters"] * look_bytes) / (hbm * 1e9) * 1e3 / (build_ms + c["iters"] * look_ms)}}
