@@ -5,18 +5,18 @@
 // the device, one F.grid_sample launch, then cat + permute + contiguous -- 4 grid_sample launches,
 // 4 H2D copies and 2 extra passes over the (B, 324, H, W) result per RAFT iteration.
 //
-// Here: ONE launch per lookup for all levels.  A 4-warp CTA owns 32 consecutive query pixels of one
+// Here: ONE launch per lookup for all levels.  A 6-warp CTA owns 32 consecutive query pixels of one
 // level; lane = query in every phase:
-//   staging: warp w fetches rows 3w..3w+2 of each query's (2r+4)^2 neighbourhood with sector-exact
+//   staging: warp w fetches rows 2w, 2w+1 of each query's (2r+4)^2 neighbourhood with sector-exact
 //            256-bit loads (level width % 8 == 0), 128-bit loads (width % 4 == 0) or scalar loads --
 //            only the rows and sectors the taps can touch, all of a warp's loads in flight together --
 //            and parks them UNSHIFTED in a query-minor shared tile win[row][column][query]: any
 //            per-query offset is bank-conflict free.  Everything outside the slice is staged as zero
-//            (= grid_sample's zero padding).  The gather costs one DRAM access per window row
-//            (scripts/probes/gather_probe.cu: ~53 G row accesses/s on a B200), so rows are trimmed,
-//            not bytes.
+//            (= grid_sample's zero padding).  (The kernel is NOT bound by this gather: with the loads
+//            switched off it takes the same time -- DESIGN.md 2.4; its time is the chain of phases
+//            of a CTA.)
 //   taps:    the 2 x (2r+1) tap positions / fractions of every query are shared out over the warps;
-//   sample:  warp w takes the y offsets j = w, w+4, ...; every store of out[b, l*81 + k, q] is a full
+//   sample:  warp w takes the y offsets j = w, w+6, ...; every store of out[b, l*81 + k, q] is a full
 //            128-byte line; the result is written once, in its final (B, L*(2r+1)^2, H, W) layout.
 // Channel order k = i*(2r+1) + j with i the x offset and j the y offset (corr.py:80-86).
 //
@@ -41,13 +41,26 @@
 namespace {
 using namespace b200lookup;
 
-// CTA = 4 warps x the same 32 queries of one level; lane = query everywhere.
-//   warp w stages window rows w*RPW .. and computes every 4th tap table entry   -> one barrier
-//   warp w samples the y offsets j = w, w+4, ...                                -> 128-byte stores
+// CTA = NW (6) warps x the same 32 queries of one level; lane = query everywhere.
+//   warp w stages window rows w*RPW .. and computes every NW-th tap pair          -> one barrier
+//   warp w samples the y offsets j = w, w+NW, ...                                 -> 128-byte stores
+// Warps per CTA of the forward kernel.  6 x 2 window rows instead of 4 x 3: 78 instead of 105 registers, so the
+// same 4 CTAs per SM hold 24 warps instead of 16, and every warp's chain (loads, parking, taps, samples) is a third
+// shorter: 30.9 -> 29.8 us (KITTI), 28.3 -> 27.2 (Sintel), 35.6 -> 33.9 (FlyingThings) at B=4.  8 warps: 34.5 us (the
+// per-warp prologue is redundant work); 6 warps squeezed to 64 registers for 5 CTAs per SM: 33.1 us (spills).
+#ifndef B200_LOOKUP_NW
+#define B200_LOOKUP_NW 6
+#endif
+#ifndef B200_LOOKUP_MINB
+#define B200_LOOKUP_MINB 4        // CTAs per SM the register allocation aims at
+#endif
+constexpr int kFwdWarps = B200_LOOKUP_NW;
+
 template <int R>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(32 * kFwdWarps, B200_LOOKUP_MINB)
 lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float *__restrict__ out) {
-  constexpr int N = Geo<R>::N, WS = Geo<R>::WS, RPW = (WS + 3) / 4;
+  constexpr int NW = kFwdWarps;
+  constexpr int N = Geo<R>::N, WS = Geo<R>::WS, RPW0 = (WS + NW - 1) / NW, RPW = RPW0 < 2 ? 2 : RPW0;
   __shared__ float win[WS * kCols * 32];   // [row][column][lane]: conflict-free for any per-lane offset
   __shared__ int tab_r[2 * N][32];         // tap tables [axis * N + tap][lane]
   __shared__ float tab_a[2 * N][32];
@@ -82,15 +95,15 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
 
   // ---- this warp's window rows: all loads in flight together, parked in the tile after the tap tables
   float sv[RPW][24];
-  if (path == PATH_SECTOR) stage_load<PATH_SECTOR, RPW, WS>(a, warp * RPW, sv);
-  else if (path == PATH_HALF) stage_load_half<WS, RPW>(a, warp, sv);
-  else if (path == PATH_VEC4) stage_load<PATH_VEC4, RPW, WS>(a, warp * RPW, sv);
-  else stage_load<PATH_SCALAR, RPW, WS>(a, warp * RPW, sv);
+  if (path == PATH_SECTOR) stage_load<PATH_SECTOR, RPW, WS>(a, warp * RPW0, sv);
+  else if (path == PATH_HALF) stage_load_half<WS, RPW, NW>(a, warp, sv);
+  else if (path == PATH_VEC4) stage_load<PATH_VEC4, RPW, WS>(a, warp * RPW0, sv);
+  else stage_load<PATH_SCALAR, RPW, WS>(a, warp * RPW0, sv);
   // ---- this warp's share of the 2N tap table entries
   const float smx = (float)(a.LW - 1), smy = (float)(a.LH - 1);
   const float ismx = __frcp_rn(smx), ismy = __frcp_rn(smy);
 #pragma unroll 1
-  for (int t = warp; t < N; t += 4) {
+  for (int t = warp; t < N; t += NW) {
     int relx, rely;
     float fracx, fracy;
     two_taps<R>(cx, cy, slvl, t, smx, smy, ismx, ismy, mode, a.ox, a.oy, relx, fracx, rely, fracy);
@@ -102,10 +115,10 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
     tab_r[N + t][lane] = rely;
     tab_a[N + t][lane] = fracy;
   }
-  if (path == PATH_SECTOR) stage_store<PATH_SECTOR, RPW, WS>(win, lane, a, warp * RPW, sv);
-  else if (path == PATH_HALF) stage_store_half<WS, RPW>(win, lane, a, warp, sv);
-  else if (path == PATH_VEC4) stage_store<PATH_VEC4, RPW, WS>(win, lane, a, warp * RPW, sv);
-  else stage_store<PATH_SCALAR, RPW, WS>(win, lane, a, warp * RPW, sv);
+  if (path == PATH_SECTOR) stage_store<PATH_SECTOR, RPW, WS>(win, lane, a, warp * RPW0, sv);
+  else if (path == PATH_HALF) stage_store_half<WS, RPW, NW>(win, lane, a, warp, sv);
+  else if (path == PATH_VEC4) stage_store<PATH_VEC4, RPW, WS>(win, lane, a, warp * RPW0, sv);
+  else stage_store<PATH_SCALAR, RPW, WS>(win, lane, a, warp * RPW0, sv);
   __syncthreads();
   if (!a.q_ok) return;
 
@@ -125,7 +138,7 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
   const size_t istride = (size_t)N * p.HW;
   const float *wl = win + lane;
 #pragma unroll 1
-  for (int j = warp; j < N; j += 4) {
+  for (int j = warp; j < N; j += NW) {
     const int ry = tab_r[N + j][lane];
     const float ay = tab_a[N + j][lane], by = 1.f - ay;
     float *o = outq + (size_t)j * p.HW;
@@ -244,17 +257,22 @@ struct SectorPlan {
 
 // Backward of the lookup (what autograd derives for grid_sample): the bilinear weights of every tap,
 // times its output gradient, are added into the query's own slice of the dense gradient pyramid.
-// Same decomposition as the forward kernel: CTA = 4 warps x 32 consecutive queries of one level,
-// lane = query.  Warp w OWNS window rows 3w..3w+2: it gathers every contribution to those rows (in
+// Same decomposition as the forward kernel: CTA = 6 warps x 32 consecutive queries of one level,
+// lane = query.  Warp w OWNS window rows 2w, 2w+1 (4 warps x 3 rows: 71.0 us, 6 x 2: 67.8, 8: 71.7, 12 x 1: 80.0): it gathers every contribution to those rows (in
 // registers when the taps sit on consecutive window positions -- the common case -- else by
 // read-modify-write of its rows of the shared tile), then adds the rows into the slice with
 // sector-sized read-modify-writes.  A slice is touched by exactly one CTA per launch and a row by
 // exactly one warp: no atomics anywhere, deterministic.
+#ifndef B200_LOOKUP_BWD_NW
+#define B200_LOOKUP_BWD_NW 6      // warps per CTA of the backward kernel (each owns ceil(WS / NW) window rows): 4 -> 6 warps 71.0 -> 67.8 us
+#endif
+constexpr int kBwdWarps = B200_LOOKUP_BWD_NW;
+
 template <int R>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(32 * kBwdWarps, 4)
 lookup_bwd_kernel(const LookupParams p, const float *__restrict__ coords,
                   const float *__restrict__ gout) {
-  constexpr int N = Geo<R>::N, WS = Geo<R>::WS, RPW = (WS + 3) / 4;
+  constexpr int N = Geo<R>::N, WS = Geo<R>::WS, RPW = (WS + kBwdWarps - 1) / kBwdWarps;
   __shared__ float win[WS * kCols * 32];   // [row][column][lane]
   __shared__ int tab_r[2 * N][32];
   __shared__ float tab_a[2 * N][32];
@@ -288,7 +306,7 @@ lookup_bwd_kernel(const LookupParams p, const float *__restrict__ coords,
   const float smx = (float)(LW - 1), smy = (float)(LH - 1);
   const float ismx = __frcp_rn(smx), ismy = __frcp_rn(smy);
 #pragma unroll 1
-  for (int e = warp; e < 2 * N; e += 4) {
+  for (int e = warp; e < 2 * N; e += kBwdWarps) {
     const bool isy = e >= N;
     int rel;
     float frac;
@@ -532,10 +550,10 @@ int b200corr_lookup_forward_storage(const float *const *h_levels, int num_levels
   B200_CHECK((blocked_levels >> num_levels) == 0, "lookup_forward: blocked_levels names a level that is not there");
   dim3 grid(((p.HW + QT - 1) / QT) * num_levels, 1, B);
   switch (radius) {
-    case 1: lookup_fwd_kernel<1><<<grid, 128, 0, stream>>>(p, coords, out); break;
-    case 2: lookup_fwd_kernel<2><<<grid, 128, 0, stream>>>(p, coords, out); break;
-    case 3: lookup_fwd_kernel<3><<<grid, 128, 0, stream>>>(p, coords, out); break;
-    default: lookup_fwd_kernel<4><<<grid, 128, 0, stream>>>(p, coords, out); break;
+    case 1: lookup_fwd_kernel<1><<<grid, 32 * kFwdWarps, 0, stream>>>(p, coords, out); break;
+    case 2: lookup_fwd_kernel<2><<<grid, 32 * kFwdWarps, 0, stream>>>(p, coords, out); break;
+    case 3: lookup_fwd_kernel<3><<<grid, 32 * kFwdWarps, 0, stream>>>(p, coords, out); break;
+    default: lookup_fwd_kernel<4><<<grid, 32 * kFwdWarps, 0, stream>>>(p, coords, out); break;
   }
   B200_LAUNCH_OK("lookup_fwd_kernel");
   return 0;
@@ -555,10 +573,10 @@ int b200corr_lookup_backward(float *const *h_grad_levels, int num_levels, const 
   }
   dim3 grid(((p.HW + QT - 1) / QT) * num_levels, 1, B);
   switch (radius) {
-    case 1: lookup_bwd_kernel<1><<<grid, 128, 0, stream>>>(p, coords, grad_out); break;
-    case 2: lookup_bwd_kernel<2><<<grid, 128, 0, stream>>>(p, coords, grad_out); break;
-    case 3: lookup_bwd_kernel<3><<<grid, 128, 0, stream>>>(p, coords, grad_out); break;
-    default: lookup_bwd_kernel<4><<<grid, 128, 0, stream>>>(p, coords, grad_out); break;
+    case 1: lookup_bwd_kernel<1><<<grid, 32 * kBwdWarps, 0, stream>>>(p, coords, grad_out); break;
+    case 2: lookup_bwd_kernel<2><<<grid, 32 * kBwdWarps, 0, stream>>>(p, coords, grad_out); break;
+    case 3: lookup_bwd_kernel<3><<<grid, 32 * kBwdWarps, 0, stream>>>(p, coords, grad_out); break;
+    default: lookup_bwd_kernel<4><<<grid, 32 * kBwdWarps, 0, stream>>>(p, coords, grad_out); break;
   }
   B200_LAUNCH_OK("lookup_bwd_kernel");
   return 0;

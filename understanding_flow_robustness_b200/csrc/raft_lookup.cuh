@@ -226,15 +226,15 @@ __device__ __forceinline__ void stage_store(float *win, int lane, const StageArg
 // (oy & ~1) + 2 j, j = 0..6; warp w fetches pairs w and w + 4.  hv[jj][8 g + 4 rr + e]: packed halves 2e, 2e+1 of
 // row rr of tile column g; everything stays packed until stage_store_half, so all loads of a warp are in flight
 // together (a conversion right behind each load serialised them: 48.6 instead of 29.4 us per lookup).
-template <int WS, int NR>
+template <int WS, int NR, int NW = 4>
 __device__ __forceinline__ void stage_load_half(const StageArgs &a, int warp, float (&hv)[NR][24]) {
-  static_assert(NR >= 2 && WS / 2 + 1 <= 8, "two row pairs per warp cover the window");
+  static_assert(NR >= 2 && WS / 2 + 1 <= 2 * NW, "two row pairs per warp cover the window");
   const int c0 = a.ox & ~7, ybase = a.oy & ~1;
   const bool hi4 = (a.ox & 4) != 0;
   const int llo = hi4 ? a.clo + 4 : a.clo, lhi = hi4 ? a.chi + 4 : a.chi;
 #pragma unroll
   for (int jj = 0; jj < 2; ++jj) {
-    const int y0 = ybase + 2 * (warp + 4 * jj);
+    const int y0 = ybase + 2 * (warp + NW * jj);
 #pragma unroll
     for (int k = 0; k < 24; ++k) hv[jj][k] = 0.f;
     bool need = false;
@@ -256,7 +256,7 @@ __device__ __forceinline__ void stage_load_half(const StageArgs &a, int warp, fl
   }
 }
 
-template <int WS, int NR>
+template <int WS, int NR, int NW = 4>
 __device__ __forceinline__ void stage_store_half(float *win, int lane, const StageArgs &a, int warp, const float (&hv)[NR][24]) {
   const bool hi4 = (a.ox & 4) != 0;
   const int ybase = a.oy & ~1;
@@ -264,7 +264,7 @@ __device__ __forceinline__ void stage_store_half(float *win, int lane, const Sta
   for (int jj = 0; jj < 2; ++jj) {
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-      const int y = ybase + 2 * (warp + 4 * jj) + rr, wr = y - a.oy;
+      const int y = ybase + 2 * (warp + NW * jj) + rr, wr = y - a.oy;
       if (wr < 0 || wr >= WS) continue;
       // rows the taps do not touch / outside the level are staged as zero (the tile rows past the extent of a
       // padded level are not zero in memory)
