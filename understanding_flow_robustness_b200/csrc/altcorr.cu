@@ -10,9 +10,9 @@
 // The reference stages 32-channel tiles of both maps per 4x8 query block and loops the (2r+2)^2
 // window serially with one barrier per window point.  Here one warp owns one query: the query's
 // feature vector lives in registers (lane = channel slice), every window pixel of fmap2 is one
-// fully coalesced C*4-byte read (NHWC), the partial dot products of one window row at a time go to a
-// padded per-warp shared tile and are reduced across lanes once at the end; the 8 queries
-// of a CTA then write their (2r+1)^2 outputs as 32-byte sectors.
+// fully coalesced C*4-byte read (NHWC), all reads of a window row in flight together; the partial dot
+// products of the row are reduced across lanes by a shuffle reduce-scatter; the 8 queries of a CTA then
+// write their (2r+1)^2 outputs as 32-byte sectors.
 #include "common.cuh"
 
 namespace {
@@ -33,8 +33,7 @@ altcorr_fwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2,
                    const float *__restrict__ coords, float *__restrict__ corr, int B, int N, int H1,
                    int W1, int H2, int W2, int C) {
   using G = AGeo<R>;
-  // per-warp [window column][lane] partial sums of ONE window row (pitch 33: conflict-free both ways)
-  __shared__ float red[8][G::WN][33];
+  __shared__ float red[8][G::WN][33];      // per-warp [window column][lane] partial sums of ONE window row
   __shared__ float S[8][G::NCHUNK * 32];
   __shared__ float O[G::RD * G::RD][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -57,21 +56,32 @@ altcorr_fwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2,
     for (int i = 0; i < NV; ++i)
       if (lane + 32 * i < nvec) a[i] = p1[lane + 32 * i];
   }
+  const int rt_zero = B >> 30;   // 0 for every real batch size; the compiler cannot know
   float fxf = floorf(x), fyf = floorf(y);
   const float dx = x - fxf, dy = y - fyf;
   if (!(fabsf(fxf) < 1e8f)) fxf = -1e8f;
   if (!(fabsf(fyf) < 1e8f)) fyf = -1e8f;
   const int fx = (int)fxf, fy = (int)fyf;
 
-  // one window row at a time (a real loop: the fully unrolled 100-pixel version thrashed the
-  // instruction cache): WN coalesced pixel reads, then the row's partial dot products are reduced
-  // across lanes through the per-warp tile (lane l < WN sums column l).
-  // Measured in round 2 (scripts/time_altcorr.py, B=4, 48x160, C=256): the kernel is bound by L2->L1 bytes, not
-  // by latency or L1 hits -- branch-free rows with all 2*WN loads issued first: 0.24 ms vs 0.22 ms per level
-  // (the skipped out-of-range pixels now cost bandwidth); a __syncthreads per window row to keep the 8 queries'
-  // shared lines in L1: 0.221 vs 0.212 ms; a CTA-wide staging of the union window box in shared memory
-  // (8x8 query blocks, 8-channel chunks, cp.async double buffer): 0.31 ms (bank conflicts of the 32-byte
-  // pixel slices + two barriers per chunk).  None kept.
+  // One window row at a time (a real loop: the fully unrolled 100-pixel version thrashed the instruction cache).
+  // What bounded this kernel until late in round 2 was not L2 bandwidth (as rounds 1-2 read the 8.3 TB/s of L2 -> L1
+  // traffic; scripts/probes/l2_read_probe.cu: plain loads pull 16 TB/s out of the L2) but a chain of 100 L2 round
+  // trips per query: the compiler gave every window pixel its own branch region -- 2 loads, then the 8 FMAs that wait
+  // for them.  Now all loads of a row are issued, predicated, before the first FMA (inline PTX + a data-dependent
+  // scheduling fence, below), and the row's WN partial sums are reduced across the lanes through a per-warp tile read
+  // back by 30 lanes (three per column) instead of 10: 0.22 -> 0.18 ms per
+  // level at B=4 (10 round trips per query, 16 warps per SM at 117 registers); interior batches (warp-uniform test) use
+  // plain loads off one base pointer instead of zero-init + predicate per load, and the dot products run as packed
+  // fp32x2 FMAs: 0.18 -> 0.148 ms.  Also measured: the next row's loads issued before this row's reduction (156
+  // registers, or 128 with spills): 0.194 ms; half-row batches for 3 CTAs per SM: 0.158; 256-bit loads (two adjacent
+  // vectors per lane): 0.166; a shuffle reduce-scatter instead of the tile: 0.148 (same); round 2's earlier attempts
+  // (__syncthreads per row for L1 sharing 0.221 vs 0.212; CTA-wide staging of the union window box 0.31 ms).
+  // pixels whose loads are in flight together: the whole row while that is <= 80 registers (C <= 256), else half
+#ifndef B200_ALT_PB_FULL_NV
+#define B200_ALT_PB_FULL_NV 2
+#endif
+  constexpr int PB = NV <= B200_ALT_PB_FULL_NV ? G::WN : G::WN / 2;
+  static_assert(G::WN % PB == 0, "batches tile the window row");
 #pragma unroll 1
   for (int iy = 0; iy < G::WN; ++iy) {
     const int y2 = fy - R + iy;
@@ -79,32 +89,76 @@ altcorr_fwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2,
     const float4 *prow = reinterpret_cast<const float4 *>(f2 + (((size_t)b * H2 + (row_ok ? y2 : 0)) * W2) * C);
     float acc[G::WN];
 #pragma unroll
-    for (int ix = 0; ix < G::WN; ++ix) {
-      const int x2 = fx - R + ix;
-      float s = 0.f;
-      if (row_ok && x2 >= 0 && x2 < W2) {
-        const float4 *p2 = prow + (size_t)x2 * nvec;
+    for (int x0 = 0; x0 < G::WN; x0 += PB) {
+      float4 v[PB][NV];
+      const int xl = fx - R + x0;
+      if (row_ok && xl >= 0 && xl + PB <= W2 && nvec == 32 * NV) {
+        // interior batch, every lane loaded (warp-uniform test): plain loads off one base pointer
+        const float4 *p2 = prow + (size_t)xl * nvec + lane;
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
-          if (lane + 32 * i < nvec) {
-            const float4 v = __ldg(p2 + lane + 32 * i);
-            s = fmaf(a[i].x, v.x, s);
-            s = fmaf(a[i].y, v.y, s);
-            s = fmaf(a[i].z, v.z, s);
-            s = fmaf(a[i].w, v.w, s);
-          }
+        for (int px = 0; px < PB; ++px)
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v[px][i].x), "=f"(v[px][i].y), "=f"(v[px][i].z), "=f"(v[px][i].w)
+                         : "l"(p2 + px * nvec + 32 * i));
+      } else {
+#pragma unroll
+      for (int px = 0; px < PB; ++px) {
+        const int x2 = xl + px;
+        const bool ok = row_ok && x2 >= 0 && x2 < W2;
+        const float4 *p2 = prow + (size_t)(ok ? x2 : 0) * nvec;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int pr = (ok && lane + 32 * i < nvec) ? 1 : 0;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+              "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+              "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+              : "=f"(v[px][i].x), "=f"(v[px][i].y), "=f"(v[px][i].z), "=f"(v[px][i].w)
+              : "l"(p2 + lane + 32 * i), "r"(pr));
+        }
       }
-      acc[ix] = s;
+      }
+      // scheduling fence: every dot product starts from a zero that is COMPUTED from all of the batch's loads (their
+      // bits or-ed, & a run-time zero), so ptxas cannot sink the first FMAs in between the loads -- in-order issue
+      // would stall on them with most of the row still unrequested (it did: 4-6 loads in flight instead of 20)
+      int bits = 0;
+#pragma unroll
+      for (int px = 0; px < PB; ++px)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) bits |= __float_as_int(v[px][i].w);
+      const float dep = __int_as_float(bits & rt_zero);
+#pragma unroll
+      for (int px = 0; px < PB; ++px) {
+        // packed fp32x2 FMAs (sm_100): even and odd channels accumulate side by side, one add joins them
+        float2 s2 = make_float2(dep, 0.f);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          s2 = __ffma2_rn(make_float2(a[i].x, a[i].y), make_float2(v[px][i].x, v[px][i].y), s2);
+          s2 = __ffma2_rn(make_float2(a[i].z, a[i].w), make_float2(v[px][i].z, v[px][i].w), s2);
+        }
+        acc[x0 + px] = s2.x + s2.y;
+      }
     }
-    __syncwarp();   // previous row's readers are done with the tile
+    // cross-lane reduction of the row's WN partial sums through a per-warp tile [column][lane] (pitch 33): three lanes
+    // per column add 11 + 11 + 10 of the 32 partials each (bank = column + 11 m + t: conflict-free), two shuffles join
+    // them -- 36 instructions per row with every lane busy (a shuffle reduce-scatter: 62; ten lanes adding 32 each: 74)
+    __syncwarp();   // the previous row's readers are done with the tile
 #pragma unroll
     for (int ix = 0; ix < G::WN; ++ix) red[warp][ix][lane] = acc[ix];
     __syncwarp();
-    if (lane < G::WN) {
-      float s = 0.f;
+    {
+      const int col = lane / 3, m = lane - 3 * col;
+      float part = 0.f;
+      if (col < G::WN) {
+        const float *t = &red[warp][col][11 * m];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) s += red[warp][lane][j];
-      S[warp][iy * G::WN + lane] = s;
+        for (int k = 0; k < 10; ++k) part += t[k];
+        if (m < 2) part += t[10];
+      }
+      const float p1 = __shfl_down_sync(0xffffffffu, part, 1), p2 = __shfl_down_sync(0xffffffffu, part, 2);
+      if (m == 0 && col < G::WN) S[warp][iy * G::WN + col] = (part + p1) + p2;
     }
   }
   __syncwarp();
