@@ -263,7 +263,7 @@ altcorr_bwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2,
 }
 
 int check_alt(const char *who, int B, int N, int H1, int W1, int H2, int W2, int C, int radius) {
-  B200_CHECK(B >= 0 && N >= 1 && H1 >= 1 && W1 >= 1 && H2 >= 1 && W2 >= 1, "%s: bad sizes", who);
+  B200_CHECK(B >= 0 && B < (1 << 30) && N >= 1 && H1 >= 1 && W1 >= 1 && H2 >= 1 && W2 >= 1, "%s: bad sizes", who);   // B >> 30 is the forward kernel's run-time zero
   B200_CHECK(C >= 4 && C % 4 == 0 && C <= 128 * kMaxVec, "%s: C must be a multiple of 4, <= %d", who,
              128 * kMaxVec);
   B200_CHECK(radius >= 1 && radius <= 4, "%s: radius %d not instantiated (1..4)", who, radius);
