@@ -101,7 +101,7 @@ lookup_fwd_kernel(const LookupParams p, const float *__restrict__ coords, float 
   else stage_load<PATH_SCALAR, RPW, WS>(a, warp * RPW0, sv);
   // ---- this warp's share of the 2N tap table entries
   const float smx = (float)(a.LW - 1), smy = (float)(a.LH - 1);
-  const float ismx = __frcp_rn(smx), ismy = __frcp_rn(smy);
+  const float ismx = p.inv_w[lvl], ismy = p.inv_h[lvl];   // host-computed RN reciprocals
 #pragma unroll 1
   for (int t = warp; t < N; t += NW) {
     int relx, rely;
@@ -304,7 +304,7 @@ lookup_bwd_kernel(const LookupParams p, const float *__restrict__ coords,
         if (sp.ok[r][g]) prefetch_l2(sp.ptr[r][g]);
   }
   const float smx = (float)(LW - 1), smy = (float)(LH - 1);
-  const float ismx = __frcp_rn(smx), ismy = __frcp_rn(smy);
+  const float ismx = p.inv_w[lvl], ismy = p.inv_h[lvl];   // host-computed RN reciprocals
 #pragma unroll 1
   for (int e = warp; e < 2 * N; e += kBwdWarps) {
     const bool isy = e >= N;

@@ -19,6 +19,7 @@ struct LookupParams {
   int blocked[kMaxLevels];   // forward only: 1 = the level is stored as 8x8 tiles of 64 floats (b200corr.h), 2 = as 8x8 tiles of 64 fp16 values
   int tiles_w[kMaxLevels];   // blocked levels: tiles per row of the padded slice
   long long slice[kMaxLevels];   // floats per query slice (LH * LW, or the padded size of a blocked level)
+  float inv_w[kMaxLevels], inv_h[kMaxLevels];   // RN(1 / (LW - 1)), RN(1 / (LH - 1)): the hoisted reciprocals of the coordinate round trip
   int first_level;   // pyramid level of list entry 0: entry i has extent (H, W) >> (first_level + i), coordinate scale 2^-(first_level + i)
 };
 
@@ -295,9 +296,11 @@ inline int fill_params(LookupParams &p, const float *const *lv, float *const *gl
   p.num_levels = num_levels; p.B = B; p.HW = H * W; p.radius = radius; p.mode = mode; p.first_level = first_level;
   int h = H >> first_level, w = W >> first_level;
   for (int l = 0; l < kMaxLevels; ++l) {
+    p.inv_w[l] = 0.f; p.inv_h[l] = 0.f;
     p.lvl[l] = nullptr; p.glvl[l] = nullptr; p.LH[l] = 0; p.LW[l] = 0; p.path[l] = 0; p.blocked[l] = 0; p.tiles_w[l] = 0; p.slice[l] = 0;
     if (l < num_levels) {
       p.LH[l] = h; p.LW[l] = w; p.slice[l] = (long long)h * w;
+      p.inv_w[l] = 1.0f / (float)(w - 1); p.inv_h[l] = 1.0f / (float)(h - 1);   // IEEE division = __frcp_rn (inf for a 1-pixel axis)
       B200_CHECK(h >= 1 && w >= 1, "%s: pyramid level %d is empty (%dx%d input)", who, l, H, W);
       if (lv) { B200_CHECK(lv[l], "%s: null level %d", who, l); p.lvl[l] = lv[l]; }
       if (glv) { B200_CHECK(glv[l], "%s: null gradient level %d", who, l); p.glvl[l] = glv[l]; }
