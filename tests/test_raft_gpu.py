@@ -491,7 +491,7 @@ def test_fp16_volume_storage(shape, levels, precision):
             c = coords_grid(B, H, W, "cuda") + sigma * torch.randn(B, 2, H, W, device="cuda")
             out = a(c)
             assert torch.equal(out, rounded(c))
-            assert float((out - ref(c)).abs().max()) <= 2.0 ** -11 * vmax * 1.0001
+            assert float((out - ref(c)).abs().max()) <= 2.0 ** -11 * vmax * 1.01   # + fp32 rounding of the interpolation itself
         for r in (1, 2, 3):
             a.radius = rounded.radius = r
             c = coords_grid(B, H, W, "cuda") + 2.0 * torch.randn(B, 2, H, W, device="cuda")
