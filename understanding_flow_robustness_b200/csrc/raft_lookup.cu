@@ -306,15 +306,16 @@ lookup_bwd_kernel(const LookupParams p, const float *__restrict__ coords,
   const float smx = (float)(LW - 1), smy = (float)(LH - 1);
   const float ismx = p.inv_w[lvl], ismy = p.inv_h[lvl];   // host-computed RN reciprocals
 #pragma unroll 1
-  for (int e = warp; e < 2 * N; e += kBwdWarps) {
-    const bool isy = e >= N;
-    int rel;
-    float frac;
-    one_tap<R>(isy ? cy : cx, slvl, isy ? e - N : e, isy ? smy : smx, isy ? ismy : ismx, mode, isy ? oy : ox, rel, frac);
-    const int lo = isy ? ylo : xlo, hi = isy ? yhi : xhi;
-    if (rel >= 0 && (rel < lo || rel + 1 > hi)) { rel = -1; frac = 0.f; }   // same rule as the forward
-    tab_r[e][lane] = rel;
-    tab_a[e][lane] = frac;
+  for (int t = warp; t < N; t += kBwdWarps) {
+    int relx, rely;
+    float fracx, fracy;
+    two_taps<R>(cx, cy, slvl, t, smx, smy, ismx, ismy, mode, ox, oy, relx, fracx, rely, fracy);
+    if (relx >= 0 && (relx < xlo || relx + 1 > xhi)) { relx = -1; fracx = 0.f; }   // same rule as the forward
+    if (rely >= 0 && (rely < ylo || rely + 1 > yhi)) { rely = -1; fracy = 0.f; }
+    tab_r[t][lane] = relx;
+    tab_a[t][lane] = fracx;
+    tab_r[N + t][lane] = rely;
+    tab_a[N + t][lane] = fracy;
   }
   __syncthreads();
 
